@@ -1,0 +1,888 @@
+// K1 -- fused cross-image attention + similarity epilogue (tensor-core bound).
+//
+// One persistent, warp-specialised CTA per SM:
+//
+//   warp 0        TMA producer   Q tile (per stream) and a ring of 64-row K / V blocks
+//   warp 1        MMA issuer     tcgen05.mma: S = Q K^T (fp32, TMEM), O = P V (fp32, TMEM)
+//   warp 2        TMEM allocator
+//   warps 4-11    softmax        2 warpgroups x 128 threads; thread = one row, half the kv columns;
+//                                S (TMEM) -> exp2 -> P (16-bit, 128B-swizzled smem, the A operand of PV)
+//   warps 12-15   epilogue       O (TMEM) -> 1/l -> round to input dtype ->
+//                                  self item : keep O_self on chip (smem), accumulate |O_self|^2
+//                                  cross item: dot(O_cross,O_self), |O_cross|^2, sum (O_cross-O_self)^2
+//                                  store mode: write O to global (the SDPA replacement)
+//
+// A "stream" is (group, b, h, 128-row q tile).  The Q tile stays resident while the kv images of the
+// group stream through; the first item of a group is the query image's own K/V (the self attention
+// of diffsim/diffsim.py:179-180), whose output never leaves the SM.  The MMA warp issues
+// QK(n+1) before PV(n) so that the tensor pipe works on PV(n) while the softmax warps chew on S(n+1).
+//
+// Replaces diffsim/diffsim.py:177-197 (diffsim_xl.py:135-155, diffsim_dit.py:130-142).
+// Algorithmic work per directional attention: 4*B*H*Sq*Skv*D flops.
+#include "ds_host.h"
+#include "ds_ptx.cuh"
+
+namespace ds {
+
+enum : int { ATTN_MODE_AAS = 0, ATTN_MODE_STORE = 1 };
+
+constexpr int kAttnThreads = 512;
+constexpr int kBlockQ = 128;    // q rows per tile == TMEM lanes
+constexpr int kBlockKV = 64;    // kv rows per ring stage
+constexpr int kMaxKV = 256;     // single-pass softmax: the whole score row lives in TMEM
+constexpr int kTmemCols = 512;
+constexpr int kTmemS = 0;       // S: columns [0, 256)
+constexpr int kTmemO = 256;     // O: columns [256, 256 + D_PAD)
+constexpr int kTmemSum = 480;   // row sums: columns 480 + 2*parity + warpgroup
+constexpr int kPBytes = kBlockQ * kMaxKV * 2;  // 64 KB, four [128 x 64] 128B-swizzled sub-tiles
+
+template <int D>
+struct AttnCfg {
+  static constexpr int D_PAD = (D + 15) / 16 * 16;
+  static constexpr int SUBW = (D % 64 == 0) ? 64 : 32;           // elements per swizzle row
+  static constexpr int SUB_BYTES = SUBW * 2;                      // 128 or 64: TMA box row == swizzle span
+  static constexpr int NSUB = (D_PAD + SUBW - 1) / SUBW;
+  static constexpr uint32_t LAYOUT = (SUBW == 64) ? UMMA_SW128 : UMMA_SW64;
+  static constexpr int CPS = SUBW / 16;                           // 16-element K chunks per sub-tile
+  static constexpr int Q_SUB_BYTES = kBlockQ * SUB_BYTES;
+  static constexpr int Q_BYTES = NSUB * Q_SUB_BYTES;
+  static constexpr int KV_SUB_BYTES = kBlockKV * SUB_BYTES;
+  static constexpr int STAGE_BYTES = NSUB * KV_SUB_BYTES;
+  static constexpr int OS_BYTES = kBlockQ * D_PAD * 2;            // [D_PAD/8][128 rows][16 B]
+  static constexpr int MISC_BYTES = 2048 /*max exchange*/ + 128 /*epilogue reduce*/ + 512 /*barriers*/;
+  static constexpr int kMaxSmem = 232448;
+  static constexpr int STAGES_RAW = (kMaxSmem - Q_BYTES - OS_BYTES - kPBytes - MISC_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = Q_BYTES + OS_BYTES + kPBytes + STAGES * STAGE_BYTES + MISC_BYTES;
+  static_assert(STAGES >= 3, "not enough shared memory for the K/V ring");
+  static_assert(kTmemO + D_PAD <= kTmemSum, "TMEM budget");
+};
+
+struct AttnParams {
+  // group description (device pointers)
+  const int32_t* group_q;    // [n_groups] query image of each group
+  const int32_t* group_off;  // [n_groups + 1] entry range of each group
+  const int32_t* kv_idx;     // [n_entries] kv image of each entry
+  int n_groups;
+  int self_first;            // 1: every group starts with the query image's own K/V (AAS)
+  int mode;                  // ATTN_MODE_AAS | ATTN_MODE_STORE
+  int B, H, Sq, Skv;
+  int n_qt;                  // q tiles per (b,h)
+  int n_kb;                  // 64-row kv blocks per item
+  float scale_log2;          // softmax scale * log2(e)
+  // AAS output: part[entry][bh * n_qt + qt] = (dot, |Oc|^2, |Os|^2, sum (Oc-Os)^2)
+  float4* part;
+  // store-mode output: element strides of (b, h, s); the innermost stride is 1
+  void* out;
+  int64_t out_sb, out_sh, out_ss;
+};
+
+template <int D, bool kBf16>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_ks,
+                const __grid_constant__ CUtensorMap map_vs, const __grid_constant__ CUtensorMap map_k,
+                const __grid_constant__ CUtensorMap map_v, const AttnParams p) {
+  using C = AttnCfg<D>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sP = sQ + C::Q_BYTES;
+  uint8_t* sRing = sP + kPBytes;
+  uint8_t* sOs = sRing + C::STAGES * C::STAGE_BYTES;
+  float* sMax = reinterpret_cast<float*>(sOs + C::OS_BYTES);       // [2 parity][2 wg][128]
+  float* sRed = sMax + 512;                                        // [2 parity][4 warps][4]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 32);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* s_full = bars + 2;
+  uint64_t* s_empty = bars + 3;
+  uint64_t* p_full = bars + 4;
+  uint64_t* pv_done = bars + 5;
+  uint64_t* o_empty = bars + 6;
+  uint64_t* kv_full = bars + 8;
+  uint64_t* kv_empty = bars + 8 + C::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * C::STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("diffsim_b200: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_ks);
+    tma_prefetch_desc(&map_vs);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_v);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 256);
+    mbar_init(p_full, 256);
+    mbar_init(pv_done, 1);
+    mbar_init(o_empty, 128);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int BH = p.B * p.H;
+  const int64_t n_streams = (int64_t)p.n_groups * BH * p.n_qt;
+  const int n_kb = p.n_kb;
+
+  // stream -> (bh, group, q tile): q tile fastest so that neighbouring CTAs share K/V in L2
+#define DS_DECODE_STREAM(st)                                   \
+  const int qt = (int)((st) % p.n_qt);                         \
+  const int64_t _r = (st) / p.n_qt;                            \
+  const int g = (int)(_r % p.n_groups);                        \
+  const int bh = (int)(_r / p.n_groups);                       \
+  const int b = bh / p.H, h = bh % p.H;                        \
+  const int t0 = p.group_off[g], t1 = p.group_off[g + 1];      \
+  const int n_items = (t1 - t0) + p.self_first;                \
+  (void)b; (void)h; (void)qt;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t gi = 0;
+      bool have_prev = false;
+      int prev_img = 0, prev_b = 0, prev_h = 0;
+      bool prev_self = false;
+      auto load_block = [&](const CUtensorMap* m, int img, int bb, int hh, int j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        uint8_t* dst = sRing + (size_t)stage * C::STAGE_BYTES;
+        mbar_arrive_expect_tx(&kv_full[stage], C::STAGE_BYTES);
+#pragma unroll
+        for (int s = 0; s < C::NSUB; ++s)
+          tma_load_5d(dst + s * C::KV_SUB_BYTES, m, &kv_full[stage], s * C::SUBW, j * kBlockKV, hh, bb, img);
+        if (++stage == C::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      for (int64_t st = blockIdx.x; st < n_streams; st += gridDim.x, ++gi) {
+        DS_DECODE_STREAM(st);
+        const int qi = p.group_q[g];
+        // Q tile
+        mbar_wait(q_empty, (gi & 1) ^ 1);
+        mbar_arrive_expect_tx(q_full, C::Q_BYTES);
+#pragma unroll
+        for (int s = 0; s < C::NSUB; ++s)
+          tma_load_5d(sQ + s * C::Q_SUB_BYTES, &map_q, q_full, s * C::SUBW, qt * kBlockQ, h, b, qi);
+        for (int it = 0; it < n_items; ++it) {
+          const bool self = p.self_first && it == 0;
+          const int img = self ? qi : p.kv_idx[t0 + it - p.self_first];
+          // K blocks of this item
+          for (int j = 0; j < n_kb; ++j) load_block(self ? &map_ks : &map_k, img, b, h, j);
+          // V blocks of the previous item (the MMA warp issues QK(n+1) before PV(n))
+          if (have_prev)
+            for (int j = 0; j < n_kb; ++j) load_block(prev_self ? &map_vs : &map_v, prev_img, prev_b, prev_h, j);
+          have_prev = true;
+          prev_img = img;
+          prev_b = b;
+          prev_h = h;
+          prev_self = self;
+        }
+      }
+      if (have_prev)
+        for (int j = 0; j < n_kb; ++j) load_block(prev_self ? &map_vs : &map_v, prev_img, prev_b, prev_h, j);
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      const uint32_t fmt = kBf16 ? 1u : 0u;
+      const uint32_t idesc_qk = umma_idesc_f16(fmt, kBlockQ, kBlockKV, 0, 0);
+      const uint32_t idesc_pv = umma_idesc_f16(fmt, kBlockQ, C::D_PAD, 0, 1);
+      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP), ring_addr = smem_u32(sRing);
+      constexpr uint32_t SBO = 8 * C::SUB_BYTES;  // eight swizzle rows
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t n = 0;   // items issued by this CTA
+      uint32_t gi = 0;
+      auto advance = [&]() {
+        if (++stage == C::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      auto issue_pv = [&](uint32_t m) {
+        mbar_wait(p_full, m & 1);
+        mbar_wait(o_empty, (m & 1) ^ 1);
+        tc_fence_after_sync();
+        for (int j = 0; j < n_kb; ++j) {
+          mbar_wait(&kv_full[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t v_addr = ring_addr + stage * C::STAGE_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < kBlockKV / 16; ++kk) {
+            // A = P[:, 64 j + 16 kk ...] (K-major, 128B swizzle); B = V rows 16 kk.. (MN-major)
+            const uint64_t a_desc = umma_smem_desc(p_addr + j * (kBlockQ * 128) + kk * 32, 16, 1024, UMMA_SW128);
+            const uint64_t b_desc =
+                umma_smem_desc(v_addr + kk * 16 * C::SUB_BYTES, C::KV_SUB_BYTES, SBO, C::LAYOUT);
+            umma_f16_ss(tmem_base + kTmemO, a_desc, b_desc, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&kv_empty[stage]);
+          advance();
+        }
+        umma_commit(pv_done);
+      };
+      for (int64_t st = blockIdx.x; st < n_streams; st += gridDim.x, ++gi) {
+        DS_DECODE_STREAM(st);
+        mbar_wait(q_full, gi & 1);
+        for (int it = 0; it < n_items; ++it, ++n) {
+          // S(n) = Q K^T, one N=64 slice per kv block
+          mbar_wait(s_empty, (n & 1) ^ 1);
+          tc_fence_after_sync();
+          for (int j = 0; j < n_kb; ++j) {
+            mbar_wait(&kv_full[stage], phase);
+            tc_fence_after_sync();
+            const uint32_t k_addr = ring_addr + stage * C::STAGE_BYTES;
+#pragma unroll
+            for (int kc = 0; kc < C::D_PAD / 16; ++kc) {
+              const int sub = kc / C::CPS, off = (kc % C::CPS) * 32;
+              const uint64_t a_desc = umma_smem_desc(q_addr + sub * C::Q_SUB_BYTES + off, 16, SBO, C::LAYOUT);
+              const uint64_t b_desc = umma_smem_desc(k_addr + sub * C::KV_SUB_BYTES + off, 16, SBO, C::LAYOUT);
+              umma_f16_ss(tmem_base + kTmemS + j * kBlockKV, a_desc, b_desc, idesc_qk, kc > 0 ? 1u : 0u);
+            }
+            umma_commit(&kv_empty[stage]);
+            advance();
+          }
+          if (it == n_items - 1) umma_commit(q_empty);
+          umma_commit(s_full);
+          if (n >= 1) issue_pv(n - 1);
+        }
+      }
+      if (n >= 1) issue_pv(n - 1);
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // ------------------------------------------------------------------ softmax
+    const int wg = (warp - 4) >> 2;              // which half of the kv columns
+    const int quad = warp & 3;                   // TMEM lane quadrant this warp may touch
+    const int row = quad * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const int col0 = wg * 128;
+    const int nvalid = max(0, min(128, p.Skv - col0));  // valid kv columns in this half
+    const uint32_t p_row = smem_u32(sP) + row * 128;
+    uint32_t n = 0;
+    for (int64_t st = blockIdx.x; st < n_streams; st += gridDim.x) {
+      DS_DECODE_STREAM(st);
+      for (int it = 0; it < n_items; ++it, ++n) {
+        const uint32_t par = n & 1;
+        mbar_wait(s_full, par);
+        tc_fence_after_sync();
+        // pass 1: row maximum over this half
+        float m = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          if (c * 32 < nvalid) {
+            uint32_t v[32];
+            tmem_ld_x32(tmem_base + lane_addr + kTmemS + col0 + c * 32, v);
+            tmem_wait_ld();
+            if (c * 32 + 32 <= nvalid) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c * 32 + j < nvalid) m = fmaxf(m, __uint_as_float(v[j]));
+            }
+          }
+        }
+        m *= p.scale_log2;
+        float* mx = sMax + par * 256;
+        mx[wg * 128 + row] = m;
+        named_bar_sync(1, 256);
+        const float M = fmaxf(m, mx[(wg ^ 1) * 128 + row]);
+        // P(n) may be written once PV(n-1) has consumed P(n-1)
+        mbar_wait(pv_done, par ^ 1);
+        // pass 2: p = exp2(s * scale - M), row sum, 16-bit P into the swizzled A tile
+        float sum = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          if (c * 32 < nvalid) {
+            uint32_t v[32];
+            tmem_ld_x32(tmem_base + lane_addr + kTmemS + col0 + c * 32, v);
+            tmem_wait_ld();
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              float e0 = fast_exp2(fmaf(__uint_as_float(v[j]), p.scale_log2, -M));
+              float e1 = fast_exp2(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -M));
+              if (c * 32 + j >= nvalid) e0 = 0.f;
+              if (c * 32 + j + 1 >= nvalid) e1 = 0.f;
+              sum += e0 + e1;
+              pk[j >> 1] = pack2<kBf16>(e0, e1);
+            }
+            const int sub = (col0 + c * 32) >> 6;
+            const uint32_t base = p_row + sub * (kBlockQ * 128);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t chunk = (uint32_t)((c & 1) * 4 + q) ^ (uint32_t)(row & 7);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + chunk * 16), "r"(pk[4 * q]),
+                           "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                           : "memory");
+            }
+          } else if (c * 32 < n_kb * kBlockKV - col0) {
+            // columns beyond Skv but inside a kv block the MMA will read: P must be exactly zero
+            const int sub = (col0 + c * 32) >> 6;
+            const uint32_t base = p_row + sub * (kBlockQ * 128);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t chunk = (uint32_t)((c & 1) * 4 + q) ^ (uint32_t)(row & 7);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + chunk * 16), "r"(0u) : "memory");
+            }
+          }
+        }
+        // S(n) has been consumed: the MMA warp may overwrite it with S(n+1)
+        tc_fence_before_sync();
+        mbar_arrive(s_empty);
+        // publish the row sum (TMEM, read by the epilogue) and P (smem, read by the tensor core)
+        {
+          uint32_t sv = __float_as_uint(sum);
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tmem_base + lane_addr + kTmemSum +
+                                                                                   2 * par + wg),
+                       "r"(sv)
+                       : "memory");
+          tmem_wait_st();
+        }
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        mbar_arrive(p_full);
+      }
+    }
+  } else if (warp >= 12) {
+    // ------------------------------------------------------------------ epilogue
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const uint32_t os_row = smem_u32(sOs) + row * 16;   // chunk c lives at os_row + c * 2048
+    uint32_t n = 0;
+    float ns_tile = 0.f;  // |O_self|^2 of the current stream (meaningful on the reducing thread)
+    for (int64_t st = blockIdx.x; st < n_streams; st += gridDim.x) {
+      DS_DECODE_STREAM(st);
+      const bool row_ok = qt * kBlockQ + row < p.Sq;
+      for (int it = 0; it < n_items; ++it, ++n) {
+        const uint32_t par = n & 1;
+        const bool self = p.self_first && it == 0;
+        mbar_wait(pv_done, par);
+        tc_fence_after_sync();
+        float inv_l;
+        {
+          uint32_t s0, s1;
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];"
+                       : "=r"(s0), "=r"(s1)
+                       : "r"(tmem_base + lane_addr + kTmemSum + 2 * par)
+                       : "memory");
+          tmem_wait_ld();
+          inv_l = 1.0f / (__uint_as_float(s0) + __uint_as_float(s1));
+        }
+        float dot = 0.f, nc = 0.f, sq = 0.f;
+        uint8_t* out_row = nullptr;
+        if (p.mode == ATTN_MODE_STORE)
+          out_row = static_cast<uint8_t*>(p.out) +
+                    2 * ((int64_t)b * p.out_sb + (int64_t)h * p.out_sh + (int64_t)(qt * kBlockQ + row) * p.out_ss);
+#pragma unroll 1
+        for (int c = 0; c < C::D_PAD / 16; ++c) {
+          uint32_t v[16];
+          tmem_ld_x16(tmem_base + lane_addr + kTmemO + c * 16, v);
+          tmem_wait_ld();
+          if (c == C::D_PAD / 16 - 1) {
+            // O(n) is in registers: the MMA warp may start PV(n+1)
+            tc_fence_before_sync();
+            mbar_arrive(o_empty);
+          }
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            pk[j] = pack2<kBf16>(__uint_as_float(v[2 * j]) * inv_l, __uint_as_float(v[2 * j + 1]) * inv_l);
+          if (p.mode == ATTN_MODE_STORE) {
+            if (row_ok) {
+#pragma unroll
+              for (int hlf = 0; hlf < 2; ++hlf) {
+                if (c * 16 + hlf * 8 < D) {
+                  uint4 u = make_uint4(pk[4 * hlf], pk[4 * hlf + 1], pk[4 * hlf + 2], pk[4 * hlf + 3]);
+                  *reinterpret_cast<uint4*>(out_row + (c * 16 + hlf * 8) * 2) = u;
+                }
+              }
+            }
+          } else if (self) {
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(os_row + (2 * c + hlf) * 2048),
+                           "r"(pk[4 * hlf]), "r"(pk[4 * hlf + 1]), "r"(pk[4 * hlf + 2]), "r"(pk[4 * hlf + 3])
+                           : "memory");
+            if (row_ok) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float2 o = unpack2<kBf16>(pk[j]);
+                nc = fmaf(o.x, o.x, nc);
+                nc = fmaf(o.y, o.y, nc);
+              }
+            }
+          } else {
+            uint32_t os[8];
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf)
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(os[4 * hlf]), "=r"(os[4 * hlf + 1]), "=r"(os[4 * hlf + 2]), "=r"(os[4 * hlf + 3])
+                           : "r"(os_row + (2 * c + hlf) * 2048)
+                           : "memory");
+            if (row_ok) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float2 o = unpack2<kBf16>(pk[j]);
+                float2 s = unpack2<kBf16>(os[j]);
+                dot = fmaf(o.x, s.x, dot);
+                dot = fmaf(o.y, s.y, dot);
+                nc = fmaf(o.x, o.x, nc);
+                nc = fmaf(o.y, o.y, nc);
+                float dx = o.x - s.x, dy = o.y - s.y;
+                sq = fmaf(dx, dx, sq);
+                sq = fmaf(dy, dy, sq);
+              }
+            }
+          }
+        }
+        if (p.mode == ATTN_MODE_AAS) {
+          // fixed-order reduction over the 128 rows: shuffle tree, then warps 0..3 in order
+          dot = warp_sum(dot);
+          nc = warp_sum(nc);
+          sq = warp_sum(sq);
+          float* red = sRed + par * 16;
+          if (lane == 0) {
+            red[quad * 4 + 0] = dot;
+            red[quad * 4 + 1] = nc;
+            red[quad * 4 + 2] = sq;
+          }
+          named_bar_sync(2, 128);
+          if (quad == 0 && lane == 0) {
+            float d = red[0] + red[4] + red[8] + red[12];
+            float c2 = red[1] + red[5] + red[9] + red[13];
+            float s2 = red[2] + red[6] + red[10] + red[14];
+            if (self) {
+              ns_tile = c2;
+            } else {
+              const int t = t0 + it - p.self_first;
+              p.part[(size_t)t * (BH * p.n_qt) + bh * p.n_qt + qt] = make_float4(d, c2, ns_tile, s2);
+            }
+          }
+        }
+      }
+    }
+  }
+#undef DS_DECODE_STREAM
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// dir[t] from the per-tile partials, tiles added in index order (deterministic)
+__global__ void aas_finish_kernel(const float4* __restrict__ part, int64_t n_entries, int tiles, double E, int mode,
+                                  float* __restrict__ dir, int64_t ncols, int64_t ldd) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= n_entries) return;
+  const float4* pp = part + (size_t)t * tiles;
+  float d = 0.f, nc = 0.f, ns = 0.f, sq = 0.f;
+  for (int i = 0; i < tiles; ++i) {
+    float4 v = pp[i];
+    d += v.x;
+    nc += v.y;
+    ns += v.z;
+    sq += v.w;
+  }
+  float r;
+  if (mode == DS_SIM_MSE) r = (float)((double)sq / E);
+  else {
+    double nx = fmax(sqrt((double)nc), 1e-8), ny = fmax(sqrt((double)ns), 1e-8);
+    r = (float)((double)d / (nx * ny));
+  }
+  // optional matrix layout: entry t = row * ncols + col  ->  dir[row * ldd + col]
+  if (ncols > 0) dir[(t / ncols) * ldd + (t % ncols)] = r;
+  else dir[t] = r;
+}
+
+__global__ void single_meta_kernel(int32_t* __restrict__ meta) {
+  // group_q[0] = 0, group_off = {0, 1}, kv_idx[0] = 0
+  if (threadIdx.x < 4) meta[threadIdx.x] = (threadIdx.x == 2) ? 1 : 0;
+}
+
+__global__ void pairs_setup_kernel(const int32_t* __restrict__ pair_idx, int64_t n_pairs, int32_t* __restrict__ group_q,
+                                   int32_t* __restrict__ group_off, int32_t* __restrict__ kv_idx) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < 2 * n_pairs) {
+    int64_t pr = i >> 1;
+    int s = (int)(i & 1);
+    group_q[i] = pair_idx[2 * pr + s];
+    kv_idx[i] = pair_idx[2 * pr + (s ^ 1)];
+    group_off[i] = (int32_t)i;
+  }
+  if (i == 2 * n_pairs) group_off[i] = (int32_t)i;
+}
+
+__global__ void pairs_finish_kernel(const float* __restrict__ dir, int64_t n_pairs, float* __restrict__ scores) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n_pairs) scores[i] = (dir[2 * i] + dir[2 * i + 1]) * 0.5f;
+}
+
+__global__ void matrix_setup_kernel(int64_t n_rows, int64_t n_cols, int chunks, int64_t chunk_cols,
+                                    int32_t* __restrict__ group_q, int32_t* __restrict__ group_off,
+                                    int32_t* __restrict__ kv_idx) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t n_groups = n_rows * chunks;
+  if (i < n_rows * n_cols) kv_idx[i] = (int32_t)(i % n_cols);
+  if (i < n_groups) {
+    int64_t r = i / chunks, ch = i % chunks;
+    group_q[i] = (int32_t)r;
+    group_off[i] = (int32_t)(r * n_cols + min(n_cols, ch * chunk_cols));
+  }
+  if (i == n_groups) group_off[i] = (int32_t)(n_rows * n_cols);
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static int check_t5(const ds_tensor5& t, const char* name) {
+  if (!t.ptr) return fail(DS_ERR_INVALID, "%s: null pointer", name);
+  if (t.dtype != DS_F16 && t.dtype != DS_BF16) return fail(DS_ERR_UNSUPPORTED, "%s: dtype must be f16 or bf16", name);
+  for (int i = 0; i < 5; ++i)
+    if (t.size[i] <= 0) return fail(DS_ERR_INVALID, "%s: size[%d] = %lld", name, i, (long long)t.size[i]);
+  if (t.stride[4] != 1) return fail(DS_ERR_INVALID, "%s: innermost stride must be 1 (got %lld)", name, (long long)t.stride[4]);
+  if ((uintptr_t)t.ptr & 15) return fail(DS_ERR_INVALID, "%s: base pointer must be 16-byte aligned", name);
+  for (int i = 0; i < 4; ++i) {
+    if (t.size[i] > 1 && (t.stride[i] <= 0 || (t.stride[i] & 7)))
+      return fail(DS_ERR_INVALID, "%s: stride[%d] = %lld must be a positive multiple of 8 elements (16 bytes)", name, i,
+                  (long long)t.stride[i]);
+  }
+  if (t.size[0] > INT32_MAX || t.size[3] > INT32_MAX) return fail(DS_ERR_INVALID, "%s: too large", name);
+  return DS_OK;
+}
+
+static int make_map(CUtensorMap* m, const ds_tensor5& t, int subw, int rows) {
+  // TMA dims, fastest first: (d, s, h, b, n)
+  uint64_t dims[5] = {(uint64_t)t.size[4], (uint64_t)t.size[3], (uint64_t)t.size[2], (uint64_t)t.size[1],
+                      (uint64_t)t.size[0]};
+  auto st = [&](int i) -> uint64_t {
+    // a size-1 dimension may carry any stride; give it a harmless 16-byte one
+    int64_t s = t.size[i] > 1 ? t.stride[i] : 8;
+    return (uint64_t)s * 2;
+  };
+  uint64_t strides[4] = {st(3), st(2), st(1), st(0)};
+  uint32_t box[5] = {(uint32_t)subw, (uint32_t)rows, 1, 1, 1};
+  return encode_tensor_map(m, t.dtype, 5, t.ptr, dims, strides, box, subw * 2);
+}
+
+struct AttnLaunch {
+  ds_tensor5 q, ks, vs, k, v;
+  AttnParams p;
+};
+
+template <int D>
+static int launch_attn_d(const AttnLaunch& a, cudaStream_t st) {
+  using C = AttnCfg<D>;
+  CUtensorMap mq, mks, mvs, mk, mv;
+  int rc;
+  if ((rc = make_map(&mq, a.q, C::SUBW, kBlockQ)) != DS_OK) return rc;
+  if ((rc = make_map(&mks, a.ks, C::SUBW, kBlockKV)) != DS_OK) return rc;
+  if ((rc = make_map(&mvs, a.vs, C::SUBW, kBlockKV)) != DS_OK) return rc;
+  if ((rc = make_map(&mk, a.k, C::SUBW, kBlockKV)) != DS_OK) return rc;
+  if ((rc = make_map(&mv, a.v, C::SUBW, kBlockKV)) != DS_OK) return rc;
+  const int64_t n_streams = (int64_t)a.p.n_groups * a.p.B * a.p.H * a.p.n_qt;
+  int grid = sm_count();
+  if (n_streams < grid) grid = (int)n_streams;
+  if (grid <= 0) return DS_OK;
+  if (a.q.dtype == DS_BF16) {
+    DS_CUDA_TRY(cudaFuncSetAttribute(aas_attn_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    aas_attn_kernel<D, true><<<grid, kAttnThreads, C::SMEM_BYTES, st>>>(mq, mks, mvs, mk, mv, a.p);
+  } else {
+    DS_CUDA_TRY(cudaFuncSetAttribute(aas_attn_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    aas_attn_kernel<D, false><<<grid, kAttnThreads, C::SMEM_BYTES, st>>>(mq, mks, mvs, mk, mv, a.p);
+  }
+  DS_CUDA_TRY(cudaGetLastError());
+  return DS_OK;
+}
+
+static int launch_attn(const AttnLaunch& a, cudaStream_t st) {
+  switch ((int)a.q.size[4]) {
+    case 40: return launch_attn_d<40>(a, st);
+    case 64: return launch_attn_d<64>(a, st);
+    case 72: return launch_attn_d<72>(a, st);
+    case 80: return launch_attn_d<80>(a, st);
+    case 128: return launch_attn_d<128>(a, st);
+    case 160: return launch_attn_d<160>(a, st);
+    default:
+      return fail(DS_ERR_UNSUPPORTED, "head dim %lld is not built (supported: 40, 64, 72, 80, 128, 160)",
+                  (long long)a.q.size[4]);
+  }
+}
+
+// common validation of a (q, k_self, v_self, k, v) set; fills the shape part of AttnParams
+static int prepare(AttnLaunch& a, float scale, const char* who) {
+  int rc;
+  if ((rc = check_t5(a.q, "q")) != DS_OK) return rc;
+  if ((rc = check_t5(a.ks, "k_self")) != DS_OK) return rc;
+  if ((rc = check_t5(a.vs, "v_self")) != DS_OK) return rc;
+  if ((rc = check_t5(a.k, "k")) != DS_OK) return rc;
+  if ((rc = check_t5(a.v, "v")) != DS_OK) return rc;
+  const ds_tensor5* all[5] = {&a.q, &a.ks, &a.vs, &a.k, &a.v};
+  for (int i = 1; i < 5; ++i) {
+    if (all[i]->dtype != a.q.dtype) return fail(DS_ERR_INVALID, "%s: all tensors must share one dtype", who);
+    if (all[i]->size[1] != a.q.size[1] || all[i]->size[2] != a.q.size[2] || all[i]->size[4] != a.q.size[4])
+      return fail(DS_ERR_INVALID, "%s: B, H and D must match across q, k, v", who);
+  }
+  if (a.ks.size[3] != a.k.size[3] || a.vs.size[3] != a.k.size[3] || a.v.size[3] != a.k.size[3])
+    return fail(DS_ERR_INVALID, "%s: all key/value tensors must share the kv length", who);
+  if (a.ks.size[0] != a.q.size[0] || a.vs.size[0] != a.q.size[0])
+    return fail(DS_ERR_INVALID, "%s: k_self / v_self must hold the same images as q", who);
+  if (a.k.size[0] != a.v.size[0]) return fail(DS_ERR_INVALID, "%s: k and v must hold the same images", who);
+  const int64_t Skv = a.k.size[3];
+  if (Skv > kMaxKV)
+    return fail(DS_ERR_UNSUPPORTED, "%s: kv length %lld > %d is not built yet (single-pass softmax kernel)", who,
+                (long long)Skv, kMaxKV);
+  const int64_t D = a.q.size[4];
+  a.p.B = (int)a.q.size[1];
+  a.p.H = (int)a.q.size[2];
+  a.p.Sq = (int)a.q.size[3];
+  a.p.Skv = (int)Skv;
+  a.p.n_qt = (int)((a.q.size[3] + kBlockQ - 1) / kBlockQ);
+  a.p.n_kb = (int)((Skv + kBlockKV - 1) / kBlockKV);
+  const float sc = scale > 0.f ? scale : 1.0f / sqrtf((float)D);
+  a.p.scale_log2 = sc * 1.4426950408889634f;
+  return ds_device_ok();
+}
+
+static ds_tensor5 lift(const ds_tensor4& t) {
+  ds_tensor5 r;
+  r.ptr = t.ptr;
+  r.dtype = t.dtype;
+  r.size[0] = 1;
+  r.stride[0] = 8;
+  for (int i = 0; i < 4; ++i) {
+    r.size[i + 1] = t.size[i];
+    r.stride[i + 1] = t.stride[i];
+  }
+  return r;
+}
+
+}  // namespace ds
+
+extern "C" {
+
+size_t ds_attn_fwd_workspace_bytes(ds_tensor4 q, ds_tensor4 k) {
+  (void)q;
+  (void)k;
+  return 1024;
+}
+
+int ds_attn_fwd(ds_tensor4 q, ds_tensor4 k, ds_tensor4 v, float scale, ds_tensor4 out, void* ws, size_t ws_bytes,
+                void* stream) {
+  using namespace ds;
+  AttnLaunch a;
+  a.q = lift(q);
+  a.k = lift(k);
+  a.v = lift(v);
+  a.ks = a.k;
+  a.vs = a.v;
+  // k_self / v_self are unused in store mode, but must pass validation: give them q's image count
+  int rc = prepare(a, scale, "ds_attn_fwd");
+  if (rc != DS_OK) return rc;
+  if (!out.ptr || out.dtype != q.dtype) return fail(DS_ERR_INVALID, "ds_attn_fwd: out must have q's dtype");
+  for (int i = 0; i < 4; ++i)
+    if (out.size[i] != q.size[i]) return fail(DS_ERR_INVALID, "ds_attn_fwd: out must have q's shape");
+  if (out.stride[3] != 1 || ((uintptr_t)out.ptr & 15) || (out.stride[0] & 7) || (out.stride[1] & 7) || (out.stride[2] & 7))
+    return fail(DS_ERR_INVALID, "ds_attn_fwd: out needs a unit innermost stride and 16-byte aligned rows");
+  Workspace w(ws, ws_bytes);
+  int32_t* meta = static_cast<int32_t*>(w.take(4 * sizeof(int32_t)));
+  if (!meta) return fail(DS_ERR_WORKSPACE, "ds_attn_fwd: workspace too small (need %zu bytes)", (size_t)1024);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // one group: query image 0, one entry: kv image 0
+  single_meta_kernel<<<1, 32, 0, st>>>(meta);
+  DS_CUDA_TRY(cudaGetLastError());
+  a.p.group_q = meta;
+  a.p.group_off = meta + 1;
+  a.p.kv_idx = meta + 3;
+  a.p.n_groups = 1;
+  a.p.self_first = 0;
+  a.p.mode = ATTN_MODE_STORE;
+  a.p.part = nullptr;
+  a.p.out = out.ptr;
+  a.p.out_sb = out.stride[0];
+  a.p.out_sh = out.stride[1];
+  a.p.out_ss = out.stride[2];
+  return launch_attn(a, st);
+}
+
+size_t ds_aas_groups_workspace_bytes(ds_tensor5 q, int64_t n_groups, int64_t n_entries) {
+  (void)n_groups;
+  if (n_entries <= 0) return 256;
+  const int64_t tiles = q.size[1] * q.size[2] * ((q.size[3] + ds::kBlockQ - 1) / ds::kBlockQ);
+  return ds::align_up((size_t)n_entries * tiles * sizeof(float4), 256) + 256;
+}
+
+int ds_aas_groups(ds_tensor5 q, ds_tensor5 k_self, ds_tensor5 v_self, ds_tensor5 k, ds_tensor5 v,
+                  const int32_t* group_q, const int32_t* group_off, int64_t n_groups, const int32_t* kv_idx,
+                  int64_t n_entries, float scale, int mode, float* dir, void* ws, size_t ws_bytes, void* stream) {
+  using namespace ds;
+  if (n_groups < 0 || n_entries < 0) return fail(DS_ERR_INVALID, "ds_aas_groups: negative counts");
+  if (n_groups == 0 || n_entries == 0) return DS_OK;
+  if (!group_q || !group_off || !kv_idx || !dir) return fail(DS_ERR_INVALID, "ds_aas_groups: null pointer");
+  if (mode != DS_SIM_COSINE && mode != DS_SIM_MSE) return fail(DS_ERR_INVALID, "ds_aas_groups: bad mode %d", mode);
+  if (n_groups > INT32_MAX || n_entries > INT32_MAX) return fail(DS_ERR_INVALID, "ds_aas_groups: too many groups");
+  AttnLaunch a;
+  a.q = q;
+  a.ks = k_self;
+  a.vs = v_self;
+  a.k = k;
+  a.v = v;
+  int rc = prepare(a, scale, "ds_aas_groups");
+  if (rc != DS_OK) return rc;
+  const int tiles = a.p.B * a.p.H * a.p.n_qt;
+  Workspace w(ws, ws_bytes);
+  float4* part = static_cast<float4*>(w.take((size_t)n_entries * tiles * sizeof(float4)));
+  if (!part)
+    return fail(DS_ERR_WORKSPACE, "ds_aas_groups: workspace too small (%zu given, need %zu)", ws_bytes,
+                ds_aas_groups_workspace_bytes(q, n_groups, n_entries));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  a.p.group_q = group_q;
+  a.p.group_off = group_off;
+  a.p.kv_idx = kv_idx;
+  a.p.n_groups = (int)n_groups;
+  a.p.self_first = 1;
+  a.p.mode = ATTN_MODE_AAS;
+  a.p.part = part;
+  a.p.out = nullptr;
+  a.p.out_sb = a.p.out_sh = a.p.out_ss = 0;
+  rc = launch_attn(a, st);
+  if (rc != DS_OK) return rc;
+  const double E = (double)a.p.B * a.p.H * a.p.Sq * (double)q.size[4];
+  aas_finish_kernel<<<(unsigned)((n_entries + 127) / 128), 128, 0, st>>>(part, n_entries, tiles, E, mode, dir, 0, 0);
+  DS_CUDA_TRY(cudaGetLastError());
+  return DS_OK;
+}
+
+size_t ds_aas_pairs_workspace_bytes(ds_tensor5 q, int64_t n_pairs) {
+  if (n_pairs <= 0) return 256;
+  size_t b = ds_aas_groups_workspace_bytes(q, 2 * n_pairs, 2 * n_pairs);
+  b += ds::align_up((size_t)(2 * n_pairs) * 4, 256) * 2;      // group_q, kv_idx
+  b += ds::align_up((size_t)(2 * n_pairs + 1) * 4, 256);      // group_off
+  b += ds::align_up((size_t)(2 * n_pairs) * 4, 256);          // directional scores
+  return b + 256;
+}
+
+int ds_aas_pairs(ds_tensor5 q, ds_tensor5 k, ds_tensor5 v, const int32_t* pair_idx, int64_t n_pairs, float scale,
+                 int mode, float* scores, void* ws, size_t ws_bytes, void* stream) {
+  using namespace ds;
+  if (n_pairs < 0) return fail(DS_ERR_INVALID, "ds_aas_pairs: negative n_pairs");
+  if (n_pairs == 0) return DS_OK;
+  if (!pair_idx || !scores) return fail(DS_ERR_INVALID, "ds_aas_pairs: null pointer");
+  if (2 * n_pairs + 1 > INT32_MAX) return fail(DS_ERR_INVALID, "ds_aas_pairs: too many pairs");
+  Workspace w(ws, ws_bytes);
+  const int64_t G = 2 * n_pairs;
+  int32_t* gq = static_cast<int32_t*>(w.take((size_t)G * 4));
+  int32_t* kv = static_cast<int32_t*>(w.take((size_t)G * 4));
+  int32_t* go = static_cast<int32_t*>(w.take((size_t)(G + 1) * 4));
+  float* dir = static_cast<float*>(w.take((size_t)G * 4));
+  if (!gq || !kv || !go || !dir)
+    return fail(DS_ERR_WORKSPACE, "ds_aas_pairs: workspace too small (%zu given, need %zu)", ws_bytes,
+                ds_aas_pairs_workspace_bytes(q, n_pairs));
+  int rc = ds_device_ok();
+  if (rc != DS_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  pairs_setup_kernel<<<(unsigned)((G + 1 + 255) / 256), 256, 0, st>>>(pair_idx, n_pairs, gq, go, kv);
+  DS_CUDA_TRY(cudaGetLastError());
+  void* rest = w.take(0);
+  rc = ds_aas_groups(q, k, v, k, v, gq, go, G, kv, G, scale, mode, dir, rest, ws_bytes - w.off, stream);
+  if (rc != DS_OK) return rc;
+  pairs_finish_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(dir, n_pairs, scores);
+  DS_CUDA_TRY(cudaGetLastError());
+  return DS_OK;
+}
+
+static void matrix_plan(const ds_tensor5& q, int64_t n_rows, int64_t n_cols, int* chunks, int64_t* chunk_cols) {
+  const int64_t per_row = q.size[1] * q.size[2] * ((q.size[3] + ds::kBlockQ - 1) / ds::kBlockQ);
+  int64_t c = (4 * 148 + n_rows * per_row - 1) / (n_rows * per_row);  // aim at >= 4 streams per SM
+  int64_t maxc = n_cols / 8;                                          // keep the self recompute <= 1/8 of the work
+  if (c > maxc) c = maxc;
+  if (c < 1) c = 1;
+  int64_t cc = (n_cols + c - 1) / c;
+  *chunk_cols = cc;
+  *chunks = (int)((n_cols + cc - 1) / cc);
+}
+
+size_t ds_aas_matrix_workspace_bytes(ds_tensor5 q, ds_tensor5 k) {
+  const int64_t nr = q.size[0], nc = k.size[0];
+  if (nr <= 0 || nc <= 0) return 256;
+  int chunks;
+  int64_t cc;
+  matrix_plan(q, nr, nc, &chunks, &cc);
+  size_t b = ds_aas_groups_workspace_bytes(q, nr * chunks, nr * nc);
+  b += ds::align_up((size_t)(nr * chunks) * 4, 256);
+  b += ds::align_up((size_t)(nr * chunks + 1) * 4, 256);
+  b += ds::align_up((size_t)(nr * nc) * 4, 256);
+  return b + 256;
+}
+
+int ds_aas_matrix(ds_tensor5 q, ds_tensor5 k_self, ds_tensor5 v_self, ds_tensor5 k, ds_tensor5 v, float scale, int mode,
+                  float* Dm, int64_t ldd, void* ws, size_t ws_bytes, void* stream) {
+  using namespace ds;
+  const int64_t nr = q.size[0], nc = k.size[0];
+  if (nr <= 0 || nc <= 0) return fail(DS_ERR_INVALID, "ds_aas_matrix: empty image set");
+  if (!Dm || ldd < nc) return fail(DS_ERR_INVALID, "ds_aas_matrix: null output or ldd < columns");
+  if (mode != DS_SIM_COSINE && mode != DS_SIM_MSE) return fail(DS_ERR_INVALID, "ds_aas_matrix: bad mode %d", mode);
+  if (nr * nc > INT32_MAX) return fail(DS_ERR_INVALID, "ds_aas_matrix: more than 2^31 entries; split the rows");
+  int chunks;
+  int64_t cc;
+  matrix_plan(q, nr, nc, &chunks, &cc);
+  const int64_t G = nr * chunks, T = nr * nc;
+  AttnLaunch a;
+  a.q = q;
+  a.ks = k_self;
+  a.vs = v_self;
+  a.k = k;
+  a.v = v;
+  int rc = prepare(a, scale, "ds_aas_matrix");
+  if (rc != DS_OK) return rc;
+  const int tiles = a.p.B * a.p.H * a.p.n_qt;
+  Workspace w(ws, ws_bytes);
+  int32_t* gq = static_cast<int32_t*>(w.take((size_t)G * 4));
+  int32_t* go = static_cast<int32_t*>(w.take((size_t)(G + 1) * 4));
+  int32_t* kv = static_cast<int32_t*>(w.take((size_t)T * 4));
+  float4* part = static_cast<float4*>(w.take((size_t)T * tiles * sizeof(float4)));
+  if (!gq || !go || !kv || !part)
+    return fail(DS_ERR_WORKSPACE, "ds_aas_matrix: workspace too small (%zu given, need %zu)", ws_bytes,
+                ds_aas_matrix_workspace_bytes(q, k));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t setup_n = (T > G + 1 ? T : G + 1);
+  matrix_setup_kernel<<<(unsigned)((setup_n + 255) / 256), 256, 0, st>>>(nr, nc, chunks, cc, gq, go, kv);
+  DS_CUDA_TRY(cudaGetLastError());
+  a.p.group_q = gq;
+  a.p.group_off = go;
+  a.p.kv_idx = kv;
+  a.p.n_groups = (int)G;
+  a.p.self_first = 1;
+  a.p.mode = ATTN_MODE_AAS;
+  a.p.part = part;
+  a.p.out = nullptr;
+  a.p.out_sb = a.p.out_sh = a.p.out_ss = 0;
+  rc = launch_attn(a, st);
+  if (rc != DS_OK) return rc;
+  const double E = (double)a.p.B * a.p.H * a.p.Sq * (double)q.size[4];
+  aas_finish_kernel<<<(unsigned)((T + 127) / 128), 128, 0, st>>>(part, T, tiles, E, mode, Dm, nc, ldd);
+  DS_CUDA_TRY(cudaGetLastError());
+  return DS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,373 @@
+// K3 -- N x N similarity matrix of flat feature vectors (tensor-core bound).
+//
+//   C[r,c] = sim(rows[r,:], cols[c,:])
+//
+// One tcgen05 GEMM rows x cols^T (both operands K-major, 128B-swizzled TMA tiles,
+// fp32 accumulators in TMEM), optionally split along L so that small matrices
+// still fill the 148 SMs; per-vector statistics (sum, sum of squares, min, max)
+// come from one HBM pass; a finishing kernel adds the split partials in a fixed
+// order and applies the cosine / min-max-cosine normalisation.
+//
+// All-pairs form of the flat-cosine metrics: metrics/diffeats.py:202-205,
+// metrics/clip_i.py:183, metrics/dino.py:183, metrics/vgg_gram.py:81.
+// Algorithmic work: 2 * Nr * Nc * L flops.
+#include "ds_host.h"
+#include "ds_ptx.cuh"
+
+#include <float.h>
+
+#include <type_traits>
+
+namespace ds {
+
+constexpr int kGemmBM = 128;
+constexpr int kGemmBN = 128;
+constexpr int kGemmBK = 64;                                      // 64 x 2 B = one 128-byte swizzle row
+constexpr int kGemmStages = 6;
+constexpr int kGemmABytes = kGemmBM * kGemmBK * 2;               // 16 KB
+constexpr int kGemmBBytes = kGemmBN * kGemmBK * 2;               // 16 KB
+constexpr int kGemmStageBytes = kGemmABytes + kGemmBBytes;
+constexpr int kGemmThreads = 192;                                // TMA warp, MMA warp, 4 epilogue warps
+constexpr size_t kGemmSmemBytes = 1024 + (size_t)kGemmStages * kGemmStageBytes + 256;
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+simmat_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   float* __restrict__ part, int64_t part_split_stride, int n_rows, int n_cols, int kb_total,
+                   int kb_per_split, uint32_t idesc) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kGemmStages * kGemmStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kGemmStages;
+  uint64_t* acc_full = bars + 2 * kGemmStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kGemmStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kGemmStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kGemmBN);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m0 = blockIdx.y * kGemmBM;
+  const int n0 = blockIdx.x * kGemmBN;
+  const int kb0 = blockIdx.z * kb_per_split;
+  const int kb1 = min(kb_total, kb0 + kb_per_split);
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* a = smem + (size_t)stage * kGemmStageBytes;
+        mbar_arrive_expect_tx(&full[stage], kGemmStageBytes);
+        tma_load_2d(a, &map_a, &full[stage], kb * kGemmBK, m0);
+        tma_load_2d(a + kGemmABytes, &map_b, &full[stage], kb * kGemmBK, n0);
+        if (++stage == kGemmStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after_sync();
+        const uint32_t a_addr = smem_u32(smem + (size_t)stage * kGemmStageBytes);
+        const uint64_t a_desc = umma_smem_desc(a_addr, 16, 1024, UMMA_SW128);
+        const uint64_t b_desc = umma_smem_desc(a_addr + kGemmABytes, 16, 1024, UMMA_SW128);
+#pragma unroll
+        for (int k = 0; k < kGemmBK / 16; ++k) {
+          // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in 16-byte units
+          umma_f16_ss(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == kGemmStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+    mbar_wait(acc_full, 0);
+    tc_fence_after_sync();
+    const int quad = warp & 3;
+    const int row = m0 + quad * 32 + lane;
+    float* dst = part + (size_t)blockIdx.z * part_split_stride + (size_t)row * n_cols + n0;
+#pragma unroll 1
+    for (int c = 0; c < kGemmBN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + c * 32, v);
+      tmem_wait_ld();
+      if (row < n_rows) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          int col = n0 + c * 32 + j;
+          if (col < n_cols) dst[c * 32 + j] = __uint_as_float(v[j]);
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kGemmBN);
+}
+
+// ---------------------------------------------------------------------------
+// per-vector statistics: sum, sum of squares, min, max (one HBM pass)
+// ---------------------------------------------------------------------------
+constexpr int kStatThreads = 256;
+constexpr int kStatMaxChunks = 64;
+
+template <typename T>
+__global__ void __launch_bounds__(kStatThreads)
+row_stats_kernel(const T* __restrict__ x, int64_t ld, int64_t L, int chunks, int64_t chunk_elems,
+                 float* __restrict__ partials /* [n][chunks][4] */) {
+  const int64_t row = blockIdx.x / chunks;
+  const int chunk = blockIdx.x % chunks;
+  const T* xp = x + row * ld;
+  const int64_t e0 = (int64_t)chunk * chunk_elems;
+  const int64_t e1 = min(L, e0 + chunk_elems);
+  float s = 0.f, ss = 0.f, mn = FLT_MAX, mx = -FLT_MAX;
+  const int64_t nvec = (e1 > e0) ? (e1 - e0) / 8 : 0;
+  const uint4* xv = reinterpret_cast<const uint4*>(xp + e0);
+  for (int64_t i = threadIdx.x; i < nvec; i += kStatThreads) {
+    uint4 u = __ldg(xv + i);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 f;
+      if constexpr (sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value) f = unpack2<true>(w[k]);
+      else f = unpack2<false>(w[k]);
+      s += f.x + f.y;
+      ss = fmaf(f.x, f.x, ss);
+      ss = fmaf(f.y, f.y, ss);
+      mn = fminf(mn, fminf(f.x, f.y));
+      mx = fmaxf(mx, fmaxf(f.x, f.y));
+    }
+  }
+  for (int64_t e = e0 + nvec * 8 + threadIdx.x; e < e1; e += kStatThreads) {
+    float f;
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) f = __bfloat162float(xp[e]);
+    else f = __half2float(xp[e]);
+    s += f;
+    ss = fmaf(f, f, ss);
+    mn = fminf(mn, f);
+    mx = fmaxf(mx, f);
+  }
+  __shared__ float sred[kStatThreads / 32][4];
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  mn = warp_min(mn);
+  mx = warp_max(mx);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    sred[warp][0] = s;
+    sred[warp][1] = ss;
+    sred[warp][2] = mn;
+    sred[warp][3] = mx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kStatThreads / 32; ++w) {
+      s += sred[w][0];
+      ss += sred[w][1];
+      mn = fminf(mn, sred[w][2]);
+      mx = fmaxf(mx, sred[w][3]);
+    }
+    float* dst = partials + ((size_t)row * chunks + chunk) * 4;
+    dst[0] = s;
+    dst[1] = ss;
+    dst[2] = mn;
+    dst[3] = mx;
+  }
+}
+
+// stats[n][4] (double): sum, sumsq, min, max -- chunk partials added in chunk order
+__global__ void row_stats_finish_kernel(const float* __restrict__ partials, int chunks, int64_t n,
+                                        double* __restrict__ stats) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const float* p = partials + (size_t)r * chunks * 4;
+  double s = 0.0, ss = 0.0;
+  float mn = FLT_MAX, mx = -FLT_MAX;
+  for (int c = 0; c < chunks; ++c) {
+    s += (double)p[c * 4 + 0];
+    ss += (double)p[c * 4 + 1];
+    mn = fminf(mn, p[c * 4 + 2]);
+    mx = fmaxf(mx, p[c * 4 + 3]);
+  }
+  stats[r * 4 + 0] = s;
+  stats[r * 4 + 1] = ss;
+  stats[r * 4 + 2] = (double)mn;
+  stats[r * 4 + 3] = (double)mx;
+}
+
+__global__ void simmat_finish_kernel(const float* __restrict__ part, int splits, int64_t part_split_stride,
+                                     int64_t n_rows, int64_t n_cols, const double* __restrict__ rstats,
+                                     const double* __restrict__ cstats, double L, int mode, float* __restrict__ C,
+                                     int64_t ldc) {
+  const int64_t col_blocks = (n_cols + blockDim.x - 1) / blockDim.x;
+  const int64_t r = blockIdx.x / col_blocks;
+  const int64_t c = (blockIdx.x % col_blocks) * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= n_cols || r >= n_rows) return;
+  float acc = 0.f;
+  for (int z = 0; z < splits; ++z) acc += part[(size_t)z * part_split_stride + (size_t)r * n_cols + c];
+  const double* rs = rstats + r * 4;
+  const double* cs = cstats + c * 4;
+  double out;
+  if (mode == DS_SIM_COSINE) {
+    double nx = fmax(sqrt(rs[1]), 1e-8), ny = fmax(sqrt(cs[1]), 1e-8);
+    out = (double)acc / (nx * ny);
+  } else {
+    double ax = rs[2], cx = rs[3] - rs[2], ay = cs[2], cy = cs[3] - cs[2];
+    double dot = ((double)acc - ay * rs[0] - ax * cs[0] + L * ax * ay) / (cx * cy);
+    double xx = (rs[1] - 2.0 * ax * rs[0] + L * ax * ax) / (cx * cx);
+    double yy = (cs[1] - 2.0 * ay * cs[0] + L * ay * ay) / (cy * cy);
+    double nx = fmax(sqrt(fmax(xx, 0.0)), 1e-8), ny = fmax(sqrt(fmax(yy, 0.0)), 1e-8);
+    out = dot / (nx * ny);
+  }
+  C[(size_t)r * ldc + c] = (float)out;
+}
+
+struct SimmatPlan {
+  int tiles_m, tiles_n, kb_total, splits, kb_per_split;
+  int stat_chunks;
+  int64_t stat_chunk_elems;
+};
+
+static SimmatPlan simmat_plan(int64_t n_rows, int64_t n_cols, int64_t L) {
+  SimmatPlan p;
+  p.tiles_m = (int)((n_rows + kGemmBM - 1) / kGemmBM);
+  p.tiles_n = (int)((n_cols + kGemmBN - 1) / kGemmBN);
+  p.kb_total = (int)((L + kGemmBK - 1) / kGemmBK);
+  int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
+  int64_t want = (148 + tiles - 1) / tiles;  // fill the machine once
+  if (want > 32) want = 32;
+  if (want > p.kb_total / 8) want = p.kb_total / 8;  // keep at least 8 k-blocks per split
+  if (want < 1) want = 1;
+  p.kb_per_split = (int)((p.kb_total + want - 1) / want);
+  p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  const int64_t quantum = 8 * kStatThreads;
+  int64_t c = (L + 65535) / 65536;
+  if (c > kStatMaxChunks) c = kStatMaxChunks;
+  if (c < 1) c = 1;
+  int64_t ce = (L + c - 1) / c;
+  ce = (ce + quantum - 1) / quantum * quantum;
+  p.stat_chunk_elems = ce;
+  p.stat_chunks = (int)((L + ce - 1) / ce);
+  return p;
+}
+
+}  // namespace ds
+
+extern "C" {
+
+size_t ds_simmat_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t L) {
+  using namespace ds;
+  if (n_rows <= 0 || n_cols <= 0 || L <= 0) return 256;
+  SimmatPlan p = simmat_plan(n_rows, n_cols, L);
+  size_t b = 0;
+  b += align_up((size_t)p.splits * n_rows * n_cols * sizeof(float), 256);
+  b += align_up((size_t)(n_rows + n_cols) * p.stat_chunks * 4 * sizeof(float), 256);
+  b += align_up((size_t)(n_rows + n_cols) * 4 * sizeof(double), 256);
+  return b + 1024;
+}
+
+int ds_simmat(const void* rows, int64_t n_rows, int64_t ld_rows, const void* cols, int64_t n_cols, int64_t ld_cols,
+              int64_t L, int dtype, int mode, float* C, int64_t ldc, void* ws, size_t ws_bytes, void* stream) {
+  using namespace ds;
+  if (n_rows < 0 || n_cols < 0 || L <= 0) return fail(DS_ERR_INVALID, "ds_simmat: bad sizes");
+  if (n_rows == 0 || n_cols == 0) return DS_OK;
+  if (!rows || !cols || !C) return fail(DS_ERR_INVALID, "ds_simmat: null pointer");
+  if (dtype != DS_F16 && dtype != DS_BF16) return fail(DS_ERR_UNSUPPORTED, "ds_simmat: dtype must be f16 or bf16");
+  if (mode != DS_SIM_COSINE && mode != DS_SIM_MINMAX_COSINE) return fail(DS_ERR_INVALID, "ds_simmat: bad mode %d", mode);
+  if (ld_rows < L || ld_cols < L || (ld_rows & 7) || (ld_cols & 7))
+    return fail(DS_ERR_INVALID, "ds_simmat: leading dimensions must be >= L and multiples of 8 elements");
+  if (((uintptr_t)rows & 15) || ((uintptr_t)cols & 15)) return fail(DS_ERR_INVALID, "ds_simmat: base pointers must be 16-byte aligned");
+  if (ldc < n_cols) return fail(DS_ERR_INVALID, "ds_simmat: ldc < n_cols");
+  if (n_rows > INT32_MAX || n_cols > INT32_MAX || L > (int64_t)INT32_MAX * 32) return fail(DS_ERR_INVALID, "ds_simmat: sizes too large");
+  int rc = ds_device_ok();
+  if (rc != DS_OK) return rc;
+
+  SimmatPlan p = simmat_plan(n_rows, n_cols, L);
+  Workspace w(ws, ws_bytes);
+  float* part = static_cast<float*>(w.take((size_t)p.splits * n_rows * n_cols * sizeof(float)));
+  float* spart = static_cast<float*>(w.take((size_t)(n_rows + n_cols) * p.stat_chunks * 4 * sizeof(float)));
+  double* stats = static_cast<double*>(w.take((size_t)(n_rows + n_cols) * 4 * sizeof(double)));
+  if (!part || !spart || !stats)
+    return fail(DS_ERR_WORKSPACE, "ds_simmat: workspace too small (%zu given, need %zu)", ws_bytes,
+                ds_simmat_workspace_bytes(n_rows, n_cols, L));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  // statistics pass
+  float* spart_c = spart + (size_t)n_rows * p.stat_chunks * 4;
+  double* stats_c = stats + (size_t)n_rows * 4;
+  if (dtype == DS_F16) {
+    row_stats_kernel<__half><<<(unsigned)(n_rows * p.stat_chunks), kStatThreads, 0, st>>>(
+        static_cast<const __half*>(rows), ld_rows, L, p.stat_chunks, p.stat_chunk_elems, spart);
+    row_stats_kernel<__half><<<(unsigned)(n_cols * p.stat_chunks), kStatThreads, 0, st>>>(
+        static_cast<const __half*>(cols), ld_cols, L, p.stat_chunks, p.stat_chunk_elems, spart_c);
+  } else {
+    row_stats_kernel<__nv_bfloat16><<<(unsigned)(n_rows * p.stat_chunks), kStatThreads, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(rows), ld_rows, L, p.stat_chunks, p.stat_chunk_elems, spart);
+    row_stats_kernel<__nv_bfloat16><<<(unsigned)(n_cols * p.stat_chunks), kStatThreads, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(cols), ld_cols, L, p.stat_chunks, p.stat_chunk_elems, spart_c);
+  }
+  DS_CUDA_TRY(cudaGetLastError());
+  row_stats_finish_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, st>>>(spart, p.stat_chunks, n_rows, stats);
+  row_stats_finish_kernel<<<(unsigned)((n_cols + 127) / 128), 128, 0, st>>>(spart_c, p.stat_chunks, n_cols, stats_c);
+  DS_CUDA_TRY(cudaGetLastError());
+
+  // GEMM
+  CUtensorMap map_a, map_b;
+  {
+    uint64_t dims[2] = {(uint64_t)L, (uint64_t)n_rows};
+    uint64_t str[1] = {(uint64_t)ld_rows * 2};
+    uint32_t box[2] = {(uint32_t)kGemmBK, (uint32_t)kGemmBM};
+    rc = encode_tensor_map(&map_a, dtype, 2, rows, dims, str, box, 128);
+    if (rc != DS_OK) return rc;
+    uint64_t dimsb[2] = {(uint64_t)L, (uint64_t)n_cols};
+    uint64_t strb[1] = {(uint64_t)ld_cols * 2};
+    uint32_t boxb[2] = {(uint32_t)kGemmBK, (uint32_t)kGemmBN};
+    rc = encode_tensor_map(&map_b, dtype, 2, cols, dimsb, strb, boxb, 128);
+    if (rc != DS_OK) return rc;
+  }
+  DS_CUDA_TRY(cudaFuncSetAttribute(simmat_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
+  const uint32_t idesc = umma_idesc_f16(dtype == DS_BF16 ? 1u : 0u, kGemmBM, kGemmBN, 0, 0);
+  dim3 grid(p.tiles_n, p.tiles_m, p.splits);
+  simmat_gemm_kernel<<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, part, (int64_t)n_rows * n_cols,
+                                                               (int)n_rows, (int)n_cols, p.kb_total, p.kb_per_split,
+                                                               idesc);
+  DS_CUDA_TRY(cudaGetLastError());
+
+  const int64_t fblocks = ((n_cols + 255) / 256) * n_rows;
+  if (fblocks > 0x7fffffffLL) return fail(DS_ERR_INVALID, "ds_simmat: matrix too large");
+  simmat_finish_kernel<<<(unsigned)fblocks, 256, 0, st>>>(part, p.splits, (int64_t)n_rows * n_cols, n_rows, n_cols, stats, stats_c,
+                                            (double)L, mode, C, ldc);
+  DS_CUDA_TRY(cudaGetLastError());
+  return DS_OK;
+}
+
+}  // extern "C"
