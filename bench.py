@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""Benchmark of the DiffSim AAS scoring hot path on B200 (contract: see the round prompt / DESIGN.md section 6).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps 3 --warmup 1        # the reference's CPU path on the host cores
+
+Workload (BASELINE.json configs[1]): NIGHTS-shaped 2AFC triplets (reference, left, right), SD-1.5 512^2,
+up_blocks layer 0 => Q/K/V of shape (2,8,256,160) fp16 per image, AAS + cosine.  One step scores T triplets
+(2T pairs) from a Q/K/V cache of 3T images that is resident in HBM (24 GB at T=2048: larger than the 126 MB L2,
+so every step streams its inputs from HBM).  metric = scored pairs / second, whole job.
+
+The JSON line also carries
+  roofline      the fused attention kernel: executed flops (7 directional attentions per triplet x
+                4*B*H*S*S*D) / device time of that kernel (CUDA events recorded by the library around the launch,
+                on the launching stream) vs the measured bf16 tensor peak of MEASURED_PEAKS.json
+  cpu_baseline  the reference's own torch lines (4 SDPA + 2 cosine per pair, diffsim/diffsim.py:177-197) on the
+                host cores, bounded sample
+  e2e           the same metric through HostTripletScorer: pinned host Q/K/V -> H2D copies inside the timed
+                region -> fused kernels -> decision counts read back
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SHAPE = (2, 8, 256, 160)  # SD-1.5 512^2 up_blocks layer 0
+WORKLOAD = "nights_2afc_triplets_sd15_512_up0_cosine"
+METRIC = "scored_pairs_per_sec"
+
+
+def attn_flops(shape):
+    B, H, S, D = shape
+    return 4.0 * B * H * S * S * D
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"bf16_tflops": p.get("bf16_tflops", 1590.0), "bf16_tflops_sustained": p.get("bf16_tflops_sustained", 1400.0),
+                "hbm_gbs": p.get("hbm_gbs", 6650.0), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU with nvidia-smi while the timed region runs."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int, period_s: float = 0.2):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period_s
+        self.samples, self.stop_flag = [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(self.period)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if s[3 + i].lower().startswith("active")})
+        pw = [float(s[2]) for s in self.samples if s[2].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples), "power_w_max": max(pw) if pw else None}
+
+
+def physical_gpu_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU baseline: the reference's arithmetic on the host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_pairs_per_sec(n_pairs: int, threads: int, dtype_name: str = "float16", repeats: int = 1):
+    import torch
+    from diffsim_b200 import synth
+    from oracle import aas_oracle as O
+
+    torch.set_num_threads(threads)
+    dtype = getattr(torch, dtype_name)
+    B, H, S, D = SHAPE
+    m = synth.SynthModel(B, H, S, D, seed=2334)
+    n_img = 8  # a small pool of distinct images, cycled: the cost per pair does not depend on the values
+    g = torch.Generator().manual_seed(7)
+    base = m.new_base(g)
+    imgs = [m.image(base, 0.5 + 0.06 * i, dtype, "sd", g) for i in range(n_img)]
+    # warm-up
+    for i in range(2):
+        O.reference_pair_score(*imgs[0], *imgs[1])
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        acc = 0.0
+        for p in range(n_pairs):
+            a, b = imgs[p % n_img], imgs[(p + 1 + p // n_img) % n_img]
+            acc += float(O.reference_pair_score(*a, *b))
+        best = min(best, time.perf_counter() - t0)
+    return n_pairs / best, best
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path (its torch calls), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+
+    threads = os.cpu_count() or 1
+    sample = args.cpu_pairs
+    for _ in range(max(0, args.warmup)):
+        cpu_reference_pairs_per_sec(max(8, sample // 8), threads)
+    times, vals = [], []
+    for _ in range(max(1, args.steps)):
+        v, t = cpu_reference_pairs_per_sec(sample, threads)
+        vals.append(v)
+        times.append(t)
+    value = sum(sample for _ in vals) / sum(times)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "shape_BHSD": list(SHAPE), "similarity": "cosine",
+                   "note": "reference arithmetic (4x F.scaled_dot_product_attention + 2x F.cosine_similarity per pair, "
+                           "diffsim/diffsim.py:177-197) in torch %s on the host cores; trunk not included" % torch.__version__},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} pairs per step, fp16, torch.set_num_threads({threads})"},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--triplets", type=int, default=2048, help="triplets per step per GPU (device-resident run)")
+    ap.add_argument("--e2e-triplets", type=int, default=384, help="triplets per step per GPU in the end-to-end run")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-pairs", type=int, default=512, help="pairs in the bounded CPU-baseline sample")
+    ap.add_argument("--dtype", default="float16", choices=["float16", "bfloat16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from diffsim_b200 import ops, scoring, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    dtype = getattr(torch, args.dtype)
+    B, H, S, D = SHAPE
+    T = args.triplets
+    # ---- inputs resident in HBM (weak scaling: every rank owns T triplets) -----------------------------------
+    q, k, v = synth.device_cache(B, H, S, D, 3 * T, dtype, dev, seed=1000 + rank)
+    cache = scoring.QKVCache(q, k, v)
+    trips = torch.arange(3 * T, dtype=torch.int32, device=dev).view(T, 3)
+    pairs_per_step = 2 * T
+    attn_per_step = 7 * T  # ref self + 2 cross, left self + cross, right self + cross
+
+    def step():
+        return scoring.score_triplets(cache, trips, "cosine")
+
+    for _ in range(max(3, args.warmup)):
+        ab, ac, counts, flags = step()
+    barrier()
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    ops.profile_enable(True)
+    launches0 = ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        ab, ac, counts, flags = step()
+    e1.record()
+    barrier()
+    launches = ops.LAUNCHES - launches0
+    kern_ms, kern_n = ops.profile_collect()
+    ops.profile_enable(False)
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * pairs_per_step * args.steps / (ms_total * 1e-3)
+    correct = int(counts[0].item())
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------------
+    peaks = load_peaks()
+    kern_ms_per_launch = kern_ms / max(1, kern_n)
+    achieved_tflops = attn_per_step * attn_flops(SHAPE) / (kern_ms_per_launch * 1e-3) / 1e12 if kern_n else None
+    roofline = {
+        "kernel": "aas_attn_kernel<160> (fused QK^T -> softmax -> PV -> cosine/MSE partials)",
+        "bound": "tensor", "achieved": achieved_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+        "frac": (achieved_tflops / peaks["bf16_tflops"]) if achieved_tflops else None, "traffic": None,
+        "peak_source": peaks["source"] + ", burst bf16 figure",
+        "flops_per_launch": attn_per_step * attn_flops(SHAPE), "ms_per_launch": kern_ms_per_launch,
+        "launches_timed": kern_n, "share_of_step": (kern_ms_per_launch / ms_per_step) if kern_n else None,
+    }
+
+    # ---- end to end: host buffers, H2D inside the timed region -------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        Te = args.e2e_triplets
+        host = scoring.QKVCache.empty(3 * Te, B, H, S, D, dtype, "cpu", pin=True)
+        for hm, dm in zip(host.memory(), cache.memory()):
+            hm.copy_(dm[: 3 * Te])
+        scorer = scoring.HostTripletScorer(SHAPE, dtype, dev, chunk_triplets=96)
+        scorer.score(host, Te)  # warm-up
+        scorer.score(host, Te)
+        scorer.h2d_bytes = scorer.d2h_bytes = 0
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(args.e2e_steps):
+            c_e2e = scorer.score(host, Te)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        wall = time.perf_counter() - t0
+        te = torch.tensor([max(wall * 1e3, e0.elapsed_time(e1))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * 2 * Te * args.e2e_steps / (float(te.item()) * 1e-3), "unit": "pairs/s",
+               "h2d_bytes_per_step": scorer.h2d_bytes // args.e2e_steps,
+               "d2h_bytes_per_step": scorer.d2h_bytes // args.e2e_steps,
+               "triplets_per_step_per_gpu": Te, "steps": args.e2e_steps,
+               "api": "diffsim_b200.scoring.HostTripletScorer.score (pinned host Q/K/V -> ds_aas_triplets)",
+               "correct": c_e2e[0]}
+        del host, scorer
+
+    # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v_cpu, t_cpu = cpu_reference_pairs_per_sec(args.cpu_pairs, threads)
+        cpu = {"value": v_cpu, "unit": "pairs/s", "cores": threads, "kind": "port",
+               "sample": f"{args.cpu_pairs} pairs of the same shape, fp16, reference torch calls "
+                         f"(4 SDPA + 2 cosine per pair), {t_cpu:.1f} s"}
+
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16" if dtype == torch.float16 else "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "shape_BHSD": list(SHAPE), "triplets_per_step_per_gpu": T,
+                       "pairs_per_step_per_gpu": pairs_per_step, "attentions_per_triplet": 7,
+                       "similarity": "cosine", "parallelism": f"pairs sharded over {world} rank(s), no data-path collective",
+                       "l2": f"inputs {3 * T * cache.bytes_per_image / 2**30:.1f} GiB per step > 126 MB L2 (no flush needed)"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "clocks": sampler.summary(), "correct_2afc": correct,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -16,6 +16,7 @@ DS_OK = 0
 DS_ERR_INVALID, DS_ERR_UNSUPPORTED, DS_ERR_CUDA, DS_ERR_WORKSPACE = -1, -2, -3, -4
 DS_F16, DS_BF16, DS_F32 = 0, 1, 2
 DS_SIM_COSINE, DS_SIM_MSE, DS_SIM_MINMAX_COSINE = 0, 1, 2
+DS_OPT_ROUND_SCORES = 1
 
 _ERR_NAMES = {
     DS_ERR_INVALID: "DS_ERR_INVALID",
@@ -47,12 +48,16 @@ PROTOTYPES = {
     "ds_abi_version": (_i, []),
     "ds_last_error": (C.c_char_p, []),
     "ds_device_ok": (_i, []),
+    "ds_profile_enable": (_i, [_i]),
+    "ds_profile_collect": (_i, [C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "ds_attn_fwd": (_i, [Tensor4, Tensor4, Tensor4, _f, Tensor4, _vp, _sz, _vp]),
     "ds_attn_fwd_workspace_bytes": (_sz, [Tensor4, Tensor4]),
     "ds_aas_groups": (_i, [Tensor5, Tensor5, Tensor5, Tensor5, Tensor5, _vp, _vp, _i64, _vp, _i64, _f, _i, _vp, _vp, _sz, _vp]),
     "ds_aas_groups_workspace_bytes": (_sz, [Tensor5, _i64, _i64]),
     "ds_aas_pairs": (_i, [Tensor5, Tensor5, Tensor5, _vp, _i64, _f, _i, _vp, _vp, _sz, _vp]),
     "ds_aas_pairs_workspace_bytes": (_sz, [Tensor5, _i64]),
+    "ds_aas_triplets": (_i, [Tensor5, Tensor5, Tensor5, _vp, _i64, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ds_aas_triplets_workspace_bytes": (_sz, [Tensor5, _i64]),
     "ds_aas_matrix": (_i, [Tensor5, Tensor5, Tensor5, Tensor5, Tensor5, _f, _i, _vp, _i64, _vp, _sz, _vp]),
     "ds_aas_matrix_workspace_bytes": (_sz, [Tensor5, Tensor5]),
     "ds_pair_reduce": (_i, [_vp, _vp, _i64, _i64, _i64, _i64, _i, _i, _vp, _vp, _sz, _vp]),

@@ -538,6 +538,74 @@ __global__ void pairs_finish_kernel(const float* __restrict__ dir, int64_t n_pai
   if (i < n_pairs) scores[i] = (dir[2 * i] + dir[2 * i + 1]) * 0.5f;
 }
 
+// triplet t = (ref, left, right): groups ref:[left,right], left:[ref], right:[ref]
+__global__ void triplets_setup_kernel(const int32_t* __restrict__ trip, int64_t n, int32_t* __restrict__ group_q,
+                                      int32_t* __restrict__ group_off, int32_t* __restrict__ kv_idx) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int32_t r = trip[3 * i], l = trip[3 * i + 1], rt = trip[3 * i + 2];
+    group_q[3 * i] = r;
+    group_q[3 * i + 1] = l;
+    group_q[3 * i + 2] = rt;
+    group_off[3 * i] = (int32_t)(4 * i);
+    group_off[3 * i + 1] = (int32_t)(4 * i + 2);
+    group_off[3 * i + 2] = (int32_t)(4 * i + 3);
+    kv_idx[4 * i] = l;       // ref  -> left
+    kv_idx[4 * i + 1] = rt;  // ref  -> right
+    kv_idx[4 * i + 2] = r;   // left -> ref
+    kv_idx[4 * i + 3] = r;   // right-> ref
+  }
+  if (i == n) group_off[3 * n] = (int32_t)(4 * n);
+}
+
+template <bool kBf16>
+__device__ __forceinline__ float round_like_input(float x) {
+  if constexpr (kBf16) return __bfloat162float(__float2bfloat16_rn(x));
+  else return __half2float(__float2half_rn(x));
+}
+
+// (a_on_b + b_on_a) / 2 and the drivers' strict comparisons (cute_main.py:196-205)
+template <bool kBf16>
+__global__ void triplets_finish_kernel(const float* __restrict__ dir, int64_t n, int mode, int round_scores,
+                                       float* __restrict__ ab, float* __restrict__ ac, int32_t* __restrict__ counts,
+                                       uint8_t* __restrict__ flags) {
+  int c1 = 0, c2 = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float d0 = dir[4 * i], d1 = dir[4 * i + 1], d2 = dir[4 * i + 2], d3 = dir[4 * i + 3];
+    float sab, sac;
+    if (round_scores) {
+      sab = round_like_input<kBf16>(round_like_input<kBf16>(d0) + round_like_input<kBf16>(d2)) * 0.5f;
+      sac = round_like_input<kBf16>(round_like_input<kBf16>(d1) + round_like_input<kBf16>(d3)) * 0.5f;
+      sab = round_like_input<kBf16>(sab);
+      sac = round_like_input<kBf16>(sac);
+    } else {
+      sab = (d0 + d2) * 0.5f;
+      sac = (d1 + d3) * 0.5f;
+    }
+    ab[i] = sab;
+    ac[i] = sac;
+    bool ok, ok2;
+    if (mode == DS_SIM_MSE) {
+      ok = sab < sac;
+      ok2 = sab * 2.0f < sac;
+    } else {
+      ok = sab > sac;
+      ok2 = sab > 2.0f * sac;
+    }
+    if (flags) flags[i] = ok ? 1 : 0;
+    c1 += ok ? 1 : 0;
+    c2 += ok2 ? 1 : 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+    c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (c1) atomicAdd(&counts[0], c1);
+    if (c2) atomicAdd(&counts[1], c2);
+  }
+}
+
 __global__ void matrix_setup_kernel(int64_t n_rows, int64_t n_cols, int chunks, int64_t chunk_cols,
                                     int32_t* __restrict__ group_q, int32_t* __restrict__ group_off,
                                     int32_t* __restrict__ kv_idx) {
@@ -604,6 +672,7 @@ static int launch_attn_d(const AttnLaunch& a, cudaStream_t st) {
   int grid = sm_count();
   if (n_streams < grid) grid = (int)n_streams;
   if (grid <= 0) return DS_OK;
+  profile_begin(st);
   if (a.q.dtype == DS_BF16) {
     DS_CUDA_TRY(cudaFuncSetAttribute(aas_attn_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     aas_attn_kernel<D, true><<<grid, kAttnThreads, C::SMEM_BYTES, st>>>(mq, mks, mvs, mk, mv, a.p);
@@ -611,6 +680,7 @@ static int launch_attn_d(const AttnLaunch& a, cudaStream_t st) {
     DS_CUDA_TRY(cudaFuncSetAttribute(aas_attn_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     aas_attn_kernel<D, false><<<grid, kAttnThreads, C::SMEM_BYTES, st>>>(mq, mks, mvs, mk, mv, a.p);
   }
+  profile_end(st);
   DS_CUDA_TRY(cudaGetLastError());
   return DS_OK;
 }
@@ -807,6 +877,54 @@ int ds_aas_pairs(ds_tensor5 q, ds_tensor5 k, ds_tensor5 v, const int32_t* pair_i
   rc = ds_aas_groups(q, k, v, k, v, gq, go, G, kv, G, scale, mode, dir, rest, ws_bytes - w.off, stream);
   if (rc != DS_OK) return rc;
   pairs_finish_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(dir, n_pairs, scores);
+  DS_CUDA_TRY(cudaGetLastError());
+  return DS_OK;
+}
+
+size_t ds_aas_triplets_workspace_bytes(ds_tensor5 q, int64_t n_triplets) {
+  if (n_triplets <= 0) return 256;
+  size_t b = ds_aas_groups_workspace_bytes(q, 3 * n_triplets, 4 * n_triplets);
+  b += ds::align_up((size_t)(3 * n_triplets) * 4, 256);      // group_q
+  b += ds::align_up((size_t)(3 * n_triplets + 1) * 4, 256);  // group_off
+  b += ds::align_up((size_t)(4 * n_triplets) * 4, 256) * 2;  // kv_idx, directional scores
+  return b + 256;
+}
+
+int ds_aas_triplets(ds_tensor5 q, ds_tensor5 k, ds_tensor5 v, const int32_t* trip_idx, int64_t n_triplets, float scale,
+                    int mode, int opts, float* ab, float* ac, int32_t* counts, uint8_t* flags_out, void* ws,
+                    size_t ws_bytes, void* stream) {
+  using namespace ds;
+  if (n_triplets < 0) return fail(DS_ERR_INVALID, "ds_aas_triplets: negative n_triplets");
+  if (!counts) return fail(DS_ERR_INVALID, "ds_aas_triplets: null counts");
+  if (mode != DS_SIM_COSINE && mode != DS_SIM_MSE) return fail(DS_ERR_INVALID, "ds_aas_triplets: bad mode %d", mode);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = ds_device_ok();
+  if (rc != DS_OK) return rc;
+  DS_CUDA_TRY(cudaMemsetAsync(counts, 0, 2 * sizeof(int32_t), st));
+  if (n_triplets == 0) return DS_OK;
+  if (!trip_idx || !ab || !ac) return fail(DS_ERR_INVALID, "ds_aas_triplets: null pointer");
+  if (4 * n_triplets + 1 > INT32_MAX) return fail(DS_ERR_INVALID, "ds_aas_triplets: too many triplets");
+  Workspace w(ws, ws_bytes);
+  const int64_t G = 3 * n_triplets, T = 4 * n_triplets;
+  int32_t* gq = static_cast<int32_t*>(w.take((size_t)G * 4));
+  int32_t* go = static_cast<int32_t*>(w.take((size_t)(G + 1) * 4));
+  int32_t* kv = static_cast<int32_t*>(w.take((size_t)T * 4));
+  float* dir = static_cast<float*>(w.take((size_t)T * 4));
+  if (!gq || !go || !kv || !dir)
+    return fail(DS_ERR_WORKSPACE, "ds_aas_triplets: workspace too small (%zu given, need %zu)", ws_bytes,
+                ds_aas_triplets_workspace_bytes(q, n_triplets));
+  triplets_setup_kernel<<<(unsigned)((n_triplets + 1 + 255) / 256), 256, 0, st>>>(trip_idx, n_triplets, gq, go, kv);
+  DS_CUDA_TRY(cudaGetLastError());
+  void* rest = w.take(0);
+  rc = ds_aas_groups(q, k, v, k, v, gq, go, G, kv, T, scale, mode, dir, rest, ws_bytes - w.off, stream);
+  if (rc != DS_OK) return rc;
+  int blocks = (int)((n_triplets + 255) / 256);
+  if (blocks > 1184) blocks = 1184;
+  const int rs = (opts & DS_OPT_ROUND_SCORES) ? 1 : 0;
+  if (q.dtype == DS_BF16)
+    triplets_finish_kernel<true><<<blocks, 256, 0, st>>>(dir, n_triplets, mode, rs, ab, ac, counts, flags_out);
+  else
+    triplets_finish_kernel<false><<<blocks, 256, 0, st>>>(dir, n_triplets, mode, rs, ab, ac, counts, flags_out);
   DS_CUDA_TRY(cudaGetLastError());
   return DS_OK;
 }

@@ -129,6 +129,46 @@ int encode_tensor_map(CUtensorMap* out, int dtype, int rank, const void* base, c
 }
 
 // ---------------------------------------------------------------------------
+// in-stream timing of the attention kernel
+// ---------------------------------------------------------------------------
+namespace {
+constexpr int kProfRing = 256;
+struct Prof {
+  bool on = false;
+  bool created = false;
+  cudaEvent_t ev[kProfRing][2];
+  int n = 0;
+  bool open = false;
+} g_prof;
+std::mutex g_prof_mu;
+}  // namespace
+
+void profile_begin(cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof.on || g_prof.n >= kProfRing) return;
+  if (!g_prof.created) {
+    for (int i = 0; i < kProfRing; ++i) {
+      if (cudaEventCreate(&g_prof.ev[i][0]) != cudaSuccess || cudaEventCreate(&g_prof.ev[i][1]) != cudaSuccess) {
+        (void)cudaGetLastError();
+        g_prof.on = false;
+        return;
+      }
+    }
+    g_prof.created = true;
+  }
+  cudaEventRecord(g_prof.ev[g_prof.n][0], st);
+  g_prof.open = true;
+}
+
+void profile_end(cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof.on || !g_prof.open) return;
+  cudaEventRecord(g_prof.ev[g_prof.n][1], st);
+  g_prof.n++;
+  g_prof.open = false;
+}
+
+// ---------------------------------------------------------------------------
 // 2AFC decision kernel (cute_main.py:196-205)
 // ---------------------------------------------------------------------------
 __global__ void twoafc_kernel(const float* __restrict__ ab, const float* __restrict__ ac, int64_t n, int mode,
@@ -175,6 +215,30 @@ int ds_device_ok(void) {
   }
   if (!ds::device_is_sm100())
     return ds::fail(DS_ERR_UNSUPPORTED, "current device is not compute capability 10.x (B200, sm_100a)");
+  return DS_OK;
+}
+
+int ds_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(ds::g_prof_mu);
+  ds::g_prof.on = on != 0;
+  ds::g_prof.n = 0;
+  ds::g_prof.open = false;
+  return DS_OK;
+}
+
+int ds_profile_collect(float* total_ms, int* launches) {
+  if (!total_ms || !launches) return ds::fail(DS_ERR_INVALID, "ds_profile_collect: null pointer");
+  std::lock_guard<std::mutex> lk(ds::g_prof_mu);
+  float tot = 0.f;
+  for (int i = 0; i < ds::g_prof.n; ++i) {
+    float ms = 0.f;
+    DS_CUDA_TRY(cudaEventSynchronize(ds::g_prof.ev[i][1]));
+    DS_CUDA_TRY(cudaEventElapsedTime(&ms, ds::g_prof.ev[i][0], ds::g_prof.ev[i][1]));
+    tot += ms;
+  }
+  *total_ms = tot;
+  *launches = ds::g_prof.n;
+  ds::g_prof.n = 0;
   return DS_OK;
 }
 

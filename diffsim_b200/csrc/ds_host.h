@@ -35,6 +35,10 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 int encode_tensor_map(CUtensorMap* out, int dtype, int rank, const void* base, const uint64_t* dims,
                       const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 
+// in-stream kernel timing (ds_profile_enable / ds_profile_collect)
+void profile_begin(cudaStream_t st);
+void profile_end(cudaStream_t st);
+
 // simple bump allocator over the caller's workspace
 struct Workspace {
   char* base;

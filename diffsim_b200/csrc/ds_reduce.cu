@@ -119,7 +119,7 @@ __device__ float finish_stats(const float* s, double E) {
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kRedThreads)
 pair_reduce_kernel(const T* __restrict__ x, const T* __restrict__ y, int64_t E, int64_t xs, int64_t ys,
-                   int chunks, int64_t chunk_elems, float* __restrict__ partials,
+                   int chunks, int64_t chunk_elems, int vec_ok, float* __restrict__ partials,
                    unsigned int* __restrict__ counters, float* __restrict__ out) {
   constexpr int VN = Vec16<T>::N;
   const int64_t pair = blockIdx.x / chunks;
@@ -130,8 +130,9 @@ pair_reduce_kernel(const T* __restrict__ x, const T* __restrict__ y, int64_t E, 
   const int64_t e1 = min(E, e0 + chunk_elems);
 
   Acc<MODE> acc;
-  // vector body: chunk_elems is a multiple of VN * threads * unroll, so e0 is 16-byte aligned
-  const int64_t nvec = (e1 > e0) ? (e1 - e0) / VN : 0;
+  // vector body: chunk_elems is a multiple of VN * threads * unroll, so e0 keeps the rows' 16-byte alignment;
+  // rows that are not 16-byte aligned (vec_ok == 0) take the element-wise loop below for everything
+  const int64_t nvec = (vec_ok && e1 > e0) ? (e1 - e0) / VN : 0;
   const uint4* xv = reinterpret_cast<const uint4*>(xp + e0);
   const uint4* yv = reinterpret_cast<const uint4*>(yp + e0);
   int64_t i = threadIdx.x;
@@ -243,7 +244,7 @@ static void reduce_plan(int64_t n_pairs, int64_t E, int vn, int* chunks, int64_t
 template <typename T>
 static int launch_reduce(const void* x, const void* y, int64_t n_pairs, int64_t E, int64_t xs, int64_t ys,
                          int mode, float* out, float* partials, unsigned int* counters, int chunks,
-                         int64_t chunk_elems, cudaStream_t st) {
+                         int64_t chunk_elems, int vec_ok, cudaStream_t st) {
   const T* xp = static_cast<const T*>(x);
   const T* yp = static_cast<const T*>(y);
   int64_t blocks = n_pairs * chunks;
@@ -251,16 +252,16 @@ static int launch_reduce(const void* x, const void* y, int64_t n_pairs, int64_t 
   dim3 grid((unsigned)blocks), block(kRedThreads);
   switch (mode) {
     case DS_SIM_COSINE:
-      pair_reduce_kernel<T, DS_SIM_COSINE><<<grid, block, 0, st>>>(xp, yp, E, xs, ys, chunks, chunk_elems, partials,
+      pair_reduce_kernel<T, DS_SIM_COSINE><<<grid, block, 0, st>>>(xp, yp, E, xs, ys, chunks, chunk_elems, vec_ok, partials,
                                                                    counters, out);
       break;
     case DS_SIM_MSE:
-      pair_reduce_kernel<T, DS_SIM_MSE><<<grid, block, 0, st>>>(xp, yp, E, xs, ys, chunks, chunk_elems, partials,
+      pair_reduce_kernel<T, DS_SIM_MSE><<<grid, block, 0, st>>>(xp, yp, E, xs, ys, chunks, chunk_elems, vec_ok, partials,
                                                                 counters, out);
       break;
     case DS_SIM_MINMAX_COSINE:
       pair_reduce_kernel<T, DS_SIM_MINMAX_COSINE><<<grid, block, 0, st>>>(xp, yp, E, xs, ys, chunks, chunk_elems,
-                                                                          partials, counters, out);
+                                                                          vec_ok, partials, counters, out);
       break;
     default:
       return fail(DS_ERR_INVALID, "ds_pair_reduce: bad mode %d", mode);
@@ -291,10 +292,11 @@ int ds_pair_reduce(const void* x, const void* y, int64_t n_pairs, int64_t E, int
   if (mode != DS_SIM_COSINE && mode != DS_SIM_MSE && mode != DS_SIM_MINMAX_COSINE)
     return fail(DS_ERR_INVALID, "ds_pair_reduce: bad mode %d", mode);
   const size_t es = elem_size(dtype);
-  if (((uintptr_t)x & 15) || ((uintptr_t)y & 15)) return fail(DS_ERR_INVALID, "ds_pair_reduce: x and y must be 16-byte aligned");
+  if (((uintptr_t)x % es) || ((uintptr_t)y % es)) return fail(DS_ERR_INVALID, "ds_pair_reduce: x and y must be element-aligned");
   if (x_stride < E || y_stride < E) return fail(DS_ERR_INVALID, "ds_pair_reduce: row stride smaller than E");
-  if (n_pairs > 1 && (((size_t)x_stride * es) & 15 || ((size_t)y_stride * es) & 15))
-    return fail(DS_ERR_INVALID, "ds_pair_reduce: row strides must be multiples of 16 bytes");
+  // 128-bit loads need every row to start on a 16-byte boundary; otherwise the kernel reads element-wise
+  const int vec_ok = !(((uintptr_t)x & 15) || ((uintptr_t)y & 15) ||
+                       (n_pairs > 1 && ((((size_t)x_stride * es) & 15) || (((size_t)y_stride * es) & 15))));
   int rc = ds_device_ok();
   if (rc != DS_OK) return rc;
 
@@ -310,10 +312,10 @@ int ds_pair_reduce(const void* x, const void* y, int64_t n_pairs, int64_t E, int
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DS_CUDA_TRY(cudaMemsetAsync(counters, 0, (size_t)n_pairs * sizeof(unsigned int), st));
   if (dtype == DS_F16)
-    return launch_reduce<__half>(x, y, n_pairs, E, x_stride, y_stride, mode, out, partials, counters, chunks, chunk_elems, st);
+    return launch_reduce<__half>(x, y, n_pairs, E, x_stride, y_stride, mode, out, partials, counters, chunks, chunk_elems, vec_ok, st);
   if (dtype == DS_BF16)
-    return launch_reduce<__nv_bfloat16>(x, y, n_pairs, E, x_stride, y_stride, mode, out, partials, counters, chunks, chunk_elems, st);
-  return launch_reduce<float>(x, y, n_pairs, E, x_stride, y_stride, mode, out, partials, counters, chunks, chunk_elems, st);
+    return launch_reduce<__nv_bfloat16>(x, y, n_pairs, E, x_stride, y_stride, mode, out, partials, counters, chunks, chunk_elems, vec_ok, st);
+  return launch_reduce<float>(x, y, n_pairs, E, x_stride, y_stride, mode, out, partials, counters, chunks, chunk_elems, vec_ok, st);
 }
 
 }  // extern "C"

@@ -1,0 +1,231 @@
+"""Scorers with the reference's call surface: DiffSim (SD-1.5), diffsim_xl (SDXL), diffsim_DiT (DiT-XL/2).
+
+    DiffSim(torch_dtype, device, ip_adapter).diffsim(image_A, image_B, img_size, prompt, target_block,
+        target_layer, target_step, ip_adapter=False, seed='2333', device='cuda', similarity='cosine')  -> Tensor
+    DiffSim.diffsim_value(image_A, ...) -> (q, k, v)
+    diffsim_xl(...).diffsim_score(image_A, image_B, img_size, prompt, target_block, target_layer, target_step,
+        similarity, seed)
+    diffsim_DiT(img_size, target_step, device, ckpt=None).diffsim_score(... same ...)
+
+(reference: diffsim/diffsim.py:80-258, diffsim/diffsim_xl.py:47-155, diffsim/diffsim_dit.py:29-142).
+
+What stays on PyTorch is the *trunk* -- VAE encode + one noised forward of the UNet / DiT up to the hooked layer.
+It sits behind the small `Trunk` interface: `DiffusersTrunk` drives a real diffusers pipeline when diffusers and
+weights are available (neither is, offline); `SyntheticTrunk` produces Q/K/V at the hook boundary for tests and
+benchmarks.  What is replaced is everything after the hook: the four SDPA calls and the cosine / MSE reductions
+(diffsim/diffsim.py:177-197) run as ONE fused sm_100a kernel per direction, reading the hook's strided q/k/v
+views in place.
+"""
+from __future__ import annotations
+
+import hashlib
+from typing import Optional, Sequence, Tuple, Union
+
+import torch
+
+from . import ops
+
+QKV = Tuple[torch.Tensor, torch.Tensor, torch.Tensor]
+
+
+def get_generator(seed, device):
+    """diffsim/diffsim.py:16-25 -- note the reference passes the seed through int() implicitly (default '2333')."""
+    if seed is None:
+        return None
+    if isinstance(seed, list):
+        return [torch.Generator(device).manual_seed(int(s)) for s in seed]
+    return torch.Generator(device).manual_seed(int(seed))
+
+
+def resolve_sd15_layer(target_layer, compat_layer_collapse: bool = True) -> int:
+    """`--target_layer` arrives as a list (argprocess.py nargs='+').  The reference collapses ANY single value to
+    layer 0 (diffsim/diffsim.py:99-100), so `--target_layer 5` in ipref_main.sh still scores layer 0.
+    compat_layer_collapse=True reproduces that; False gives the documented meaning (the index)."""
+    if isinstance(target_layer, int):
+        return target_layer
+    if len(target_layer) == 1:
+        return 0 if compat_layer_collapse else int(target_layer[0])
+    raise ValueError("the SD-1.5 scorer takes exactly one target layer")
+
+
+def aas_score(A: QKV, B: QKV, similarity: str = "cosine", scale: Optional[float] = None,
+              match_reference_dtype: bool = True) -> torch.Tensor:
+    """The tail of DiffSim.diffsim (diffsim/diffsim.py:177-197) on captured (q,k,v) of two images.
+
+    Two launches of the fused kernel, one per direction; each evaluates the query image's self attention and the
+    cross attention against the other image's K/V and reduces them on chip.  The q/k/v views are passed as they
+    are (unsqueeze(0) adds the image axis without copying).  With match_reference_dtype the result has the
+    reference's dtype and shape: input dtype, (1,) for cosine and () for MSE."""
+    (qa, ka, va), (qb, kb, vb) = A, B
+    one = [0]
+    off = [0, 1]
+    d_ab = ops.aas_groups(qa[None], ka[None], va[None], kb[None], vb[None], one, off, one, similarity, scale)
+    d_ba = ops.aas_groups(qb[None], kb[None], vb[None], ka[None], va[None], one, off, one, similarity, scale)
+    if not match_reference_dtype:
+        return (d_ab + d_ba) * 0.5
+    dt = qa.dtype
+    s = (d_ab.to(dt) + d_ba.to(dt)) / 2          # the reference adds two fp16/bf16 scalars
+    return s if similarity == "cosine" else s.reshape(())
+
+
+# --------------------------------------------------------------------------------------------------------
+# trunks
+# --------------------------------------------------------------------------------------------------------
+class Trunk:
+    """Everything before the hook: image -> (q, k, v) at the target layer."""
+
+    def extract(self, image, img_size, prompt, target_block, target_layer, target_step, generator) -> QKV:
+        raise NotImplementedError
+
+
+class SyntheticTrunk(Trunk):
+    """Q/K/V at the hook boundary from diffsim_b200.synth: `image` is any hashable id, or 'concept@alpha' to
+    place images of one concept at a chosen similarity."""
+
+    def __init__(self, shape=(2, 8, 256, 160), dtype=torch.float16, device="cuda", layout: str = "sd", seed: int = 2334):
+        from .synth import SynthModel
+
+        self.model = SynthModel(*shape, seed=seed)
+        self.dtype, self.device, self.layout = dtype, device, layout
+        self._bases = {}
+
+    def extract(self, image, img_size=512, prompt="", target_block="up_blocks", target_layer=0, target_step=0,
+                generator=None) -> QKV:
+        concept, _, alpha = str(image).partition("@")
+        alpha = float(alpha) if alpha else 1.0
+        h = int(hashlib.sha1(concept.encode()).hexdigest()[:8], 16)
+        if concept not in self._bases:
+            self._bases[concept] = self.model.new_base(torch.Generator().manual_seed(h))
+        g = torch.Generator().manual_seed((h ^ int(alpha * 1e6) ^ (int(target_step) << 8)) & 0x7FFFFFFF)
+        q, k, v = self.model.image(self._bases[concept], alpha, self.dtype, self.layout, g)
+        mv = lambda t: _to_device_keep_layout(t, self.device)  # noqa: E731
+        return mv(q), mv(k), mv(v)
+
+
+def _to_device_keep_layout(t: torch.Tensor, device) -> torch.Tensor:
+    """Move a strided (B,H,S,D) view to `device` preserving its strides (the head-split view layout)."""
+    out = torch.empty_strided(t.shape, t.stride(), dtype=t.dtype, device=device)
+    out.copy_(t)
+    return out
+
+
+class DiffusersTrunk(Trunk):
+    """SD-1.5 / SDXL trunk on a diffusers pipeline: VAE encode -> add noise at timesteps[target_step] -> ONE UNet
+    forward that stops at the hooked attn1 (diffsim/diffsim.py:92-96,122-155; diffsim_pipeline.py:125-221).
+    Needs `diffusers` and local weights -- neither exists offline, so this class is exercised only where they do."""
+
+    def __init__(self, pipe, device="cuda", dtype=torch.float16, guidance_scale: float = 7.5, kind: str = "sd15",
+                 value_mode: bool = False):
+        self.pipe, self.device, self.dtype, self.guidance_scale, self.kind = pipe, device, dtype, guidance_scale, kind
+        self.value_mode = value_mode
+        self._prompt_cache = {}
+
+    def target_module(self, target_block: str, target_layer):
+        unet = self.pipe.unet
+        if self.kind == "sd15":
+            # diffsim() indexes down_blocks[:-1] / up_blocks[1:]; diffsim_value() has the slices swapped
+            # (diffsim/diffsim.py:125-145 vs :224-244) -- value_mode reproduces the latter.
+            if target_block == "down_blocks":
+                blocks = unet.down_blocks[1:] if self.value_mode else unet.down_blocks[:-1]
+                return blocks[target_layer].attentions[-1].transformer_blocks[-1].attn1
+            if target_block == "mid_blocks":
+                return unet.mid_block.attentions[-1].transformer_blocks[-1].attn1
+            blocks = unet.up_blocks[:-1] if self.value_mode else unet.up_blocks[1:]
+            return blocks[target_layer].attentions[-1].transformer_blocks[-1].attn1
+        # SDXL: (block, attention, transformer_block) -- diffsim/diffsim_xl.py:88-107
+        if target_block == "down_blocks":
+            return unet.down_blocks[1:][target_layer[0]].attentions[target_layer[1]].transformer_blocks[target_layer[2]].attn1
+        if target_block == "mid_blocks":
+            return unet.mid_block.attentions[target_layer[0]].transformer_blocks[target_layer[1]].attn1
+        return unet.up_blocks[:-1][target_layer[0]].attentions[target_layer[1]].transformer_blocks[target_layer[2]].attn1
+
+    @torch.no_grad()
+    def extract(self, image, img_size, prompt, target_block, target_layer, target_step, generator) -> QKV:
+        from . import hooks
+        from .imageio import load_image, process_image
+
+        pipe = self.pipe
+        x = process_image(load_image(image), img_size).to(self.device, self.dtype)
+        latents = pipe.vae.encode(x).latent_dist.sample(generator=generator) * pipe.vae.config.scaling_factor
+        if prompt not in self._prompt_cache:
+            pe, ne = pipe.encode_prompt(prompt, self.device, 1, True, None)[:2]
+            self._prompt_cache[prompt] = torch.cat([ne, pe])
+        embeds = self._prompt_cache[prompt]
+        pipe.scheduler.set_timesteps(1000, device=self.device)
+        t = pipe.scheduler.timesteps[target_step]          # an INDEX into the 1000-step array (diffsim_pipeline.py:153-157)
+        noise = torch.randn(latents.shape, generator=generator, device=latents.device, dtype=latents.dtype)
+        noisy = pipe.scheduler.add_noise(latents, noise, t.reshape(1))
+        module = self.target_module(target_block, target_layer)
+        with hooks.capture(module, hooks.make_sd_pre_hook(early_exit=True)):
+            try:
+                pipe.unet(pipe.scheduler.scale_model_input(torch.cat([noisy] * 2), t), t, encoder_hidden_states=embeds)
+            except hooks.StopForward:
+                pass
+        return tuple(module.stores)
+
+
+# --------------------------------------------------------------------------------------------------------
+# scorers
+# --------------------------------------------------------------------------------------------------------
+class DiffSim:
+    """SD-1.5 scorer -- diffsim/diffsim.py:80-258."""
+
+    def __init__(self, torch_dtype=torch.float16, device="cuda", ip_adapter=False, trunk: Optional[Trunk] = None,
+                 match_reference_dtype: bool = True, compat_layer_collapse: bool = True):
+        if ip_adapter:
+            raise NotImplementedError("the IP-Adapter (DiffSim-C) path is not built; the reference's own hook for it "
+                                      "cannot fire (attn2 receives encoder_hidden_states as a keyword, SURVEY.md 5)")
+        self.device, self.ip_adapter, self.torch_dtype = device, ip_adapter, torch_dtype
+        self.trunk = trunk if trunk is not None else SyntheticTrunk(dtype=torch_dtype, device=device)
+        self.match_reference_dtype = match_reference_dtype
+        self.compat_layer_collapse = compat_layer_collapse
+
+    def diffsim(self, image_A, image_B, img_size, prompt, target_block, target_layer, target_step, ip_adapter=False,
+                seed="2333", device="cuda", similarity="cosine"):
+        layer = resolve_sd15_layer(target_layer, self.compat_layer_collapse)
+        generator = get_generator(seed, "cpu" if isinstance(self.trunk, SyntheticTrunk) else device)
+        A = self.trunk.extract(image_A, img_size, prompt, target_block, layer, target_step, generator)
+        B = self.trunk.extract(image_B, img_size, prompt, target_block, layer, target_step, generator)
+        return aas_score(A, B, similarity, None, self.match_reference_dtype)
+
+    def diffsim_value(self, image_A, img_size, prompt, target_block, target_layer, target_step, ip_adapter=False,
+                      seed="2333", device="cuda", similarity="cosine"):
+        layer = resolve_sd15_layer(target_layer, self.compat_layer_collapse)
+        generator = get_generator(seed, "cpu" if isinstance(self.trunk, SyntheticTrunk) else device)
+        return self.trunk.extract(image_A, img_size, prompt, target_block, layer, target_step, generator)
+
+
+class diffsim_xl:  # noqa: N801 (the reference's name)
+    """SDXL scorer -- diffsim/diffsim_xl.py:47-155.  target_layer = (block, attention, transformer_block)."""
+
+    def __init__(self, torch_dtype=torch.float16, device="cuda", ip_adapter=False, trunk: Optional[Trunk] = None,
+                 match_reference_dtype: bool = True):
+        if ip_adapter:
+            raise NotImplementedError("the IP-Adapter path is not built")
+        self.device = device
+        self.trunk = trunk if trunk is not None else SyntheticTrunk((2, 20, 256, 64), torch_dtype, device)
+        self.match_reference_dtype = match_reference_dtype
+
+    def diffsim_score(self, image_A, image_B, img_size, prompt, target_block, target_layer, target_step, similarity, seed):
+        generator = get_generator(seed, "cpu" if isinstance(self.trunk, SyntheticTrunk) else self.device)
+        A = self.trunk.extract(image_A, img_size, prompt, target_block, target_layer, target_step, generator)
+        B = self.trunk.extract(image_B, img_size, prompt, target_block, target_layer, target_step, generator)
+        return aas_score(A, B, similarity, None, self.match_reference_dtype)
+
+
+class diffsim_DiT:  # noqa: N801
+    """DiT-XL/2 scorer -- diffsim/diffsim_dit.py:29-142.  target_layer[0] = transformer block index (0..27); the hook
+    hands over q, k, v as views into the packed qkv activation, which the kernels read in place."""
+
+    def __init__(self, img_size=256, target_step=0, device="cuda", ckpt=None, trunk: Optional[Trunk] = None,
+                 match_reference_dtype: bool = True):
+        self.device = device
+        self.trunk = trunk if trunk is not None else SyntheticTrunk((2, 16, 256, 72), torch.float16, device, layout="dit")
+        self.match_reference_dtype = match_reference_dtype
+
+    def diffsim_score(self, image_A, image_B, img_size, prompt, target_block, target_layer, target_step, similarity, seed):
+        layer = target_layer[0] if not isinstance(target_layer, int) else target_layer
+        generator = get_generator(seed, "cpu" if isinstance(self.trunk, SyntheticTrunk) else self.device)
+        A = self.trunk.extract(image_A, img_size, prompt, target_block, layer, target_step, generator)
+        B = self.trunk.extract(image_B, img_size, prompt, target_block, layer, target_step, generator)
+        return aas_score(A, B, similarity, None, self.match_reference_dtype)

@@ -1,0 +1,122 @@
+"""Capture machinery at the hooked attention layer -- the replacement of diffsim/hacked_attn.py and of the
+forward-pre-hooks in diffsim/diffsim.py:43-56, diffsim_xl.py:11-24, diffsim_dit.py:19-26, metrics/hooks.py.
+
+The reference's pre-hook runs a complete hacked attention processor (projections, a full SDPA and the output
+projection whose result is thrown away, diffsim/diffsim.py:48) and then lets the module's normal forward run
+again; a new copy of the hook is registered on every call and never removed (diffsim/diffsim.py:144).  Here
+the hook computes only the three projections, leaves `module.stores = [q, k, v]` exactly as the reference does
+(same shapes, same strides: (B,H,S,D) views over (B,S,H*D) memory), can stop the trunk right after the hooked
+layer (StopForward), and is removed by its context manager.
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import Optional
+
+import torch
+
+from . import ops
+
+
+class StopForward(Exception):
+    """Raised by an early-exit hook once q, k, v of the target layer are captured: the reference lets the
+    UNet run to the end for nothing (diffsim/diffsim_pipeline.py:213-221)."""
+
+
+def split_heads(t: torch.Tensor, heads: int) -> torch.Tensor:
+    """(B,S,H*D) -> (B,H,S,D) view, as diffsim/hacked_attn.py:74-77."""
+    B, S, C = t.shape
+    return t.view(B, S, heads, C // heads).transpose(1, 2)
+
+
+def project_qkv(attn, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None):
+    """q, k, v of a diffusers-style Attention module (attributes to_q, to_k, to_v, heads; optional group_norm,
+    spatial_norm, norm_cross) -- the projection part of hacked_AttnProcessor2_0.__call__
+    (diffsim/hacked_attn.py:38-77), without the attention and output projection the reference discards."""
+    if getattr(attn, "spatial_norm", None) is not None:
+        raise NotImplementedError("spatial_norm needs temb; use B200AttnProcessor for such layers")
+    if hidden_states.ndim == 4:
+        b, c, h, w = hidden_states.shape
+        hidden_states = hidden_states.view(b, c, h * w).transpose(1, 2)
+    if getattr(attn, "group_norm", None) is not None:
+        hidden_states = attn.group_norm(hidden_states.transpose(1, 2)).transpose(1, 2)
+    query = attn.to_q(hidden_states)
+    if encoder_hidden_states is None:
+        encoder_hidden_states = hidden_states
+    elif getattr(attn, "norm_cross", False):
+        encoder_hidden_states = attn.norm_encoder_hidden_states(encoder_hidden_states)
+    key = attn.to_k(encoder_hidden_states)
+    value = attn.to_v(encoder_hidden_states)
+    return split_heads(query, attn.heads), split_heads(key, attn.heads), split_heads(value, attn.heads)
+
+
+def make_sd_pre_hook(early_exit: bool = False):
+    """forward-pre-hook with the contract of sd15_attention_forward_hooked / sdxl_attention_forward_hooked
+    (diffsim/diffsim.py:43-56): `module.stores = [query, key, value]`."""
+
+    def hook(module, input):
+        q, k, v = project_qkv(module, input[0])
+        module.stores = [q, k, v]
+        if early_exit:
+            raise StopForward()
+
+    return hook
+
+
+def make_dit_pre_hook(early_exit: bool = False):
+    """forward-pre-hook for a timm-style Attention block (attributes qkv, num_heads, head_dim, q_norm, k_norm):
+    the contract of dit_attention_forward_hook (diffsim/diffsim_dit.py:19-26).  q, k, v are views into the packed
+    qkv activation (strides (N*3*H*D, D, 3*H*D, 1)); the kernels read them in place."""
+
+    def hook(module, input):
+        x = input[0]
+        B, N, C = x.shape
+        qkv = module.qkv(x).reshape(B, N, 3, module.num_heads, module.head_dim).permute(2, 0, 3, 1, 4)
+        q, k, v = qkv.unbind(0)
+        q, k = module.q_norm(q), module.k_norm(k)
+        module.stores = [q, k, v]
+        if early_exit:
+            raise StopForward()
+
+    return hook
+
+
+@contextlib.contextmanager
+def capture(module, hook):
+    """Register `hook` as a forward-pre-hook on `module` for the duration of the block (and remove it: the
+    reference accumulates one more hook per call, diffsim/diffsim.py:144)."""
+    handle = module.register_forward_pre_hook(hook)
+    try:
+        yield module
+    finally:
+        handle.remove()
+
+
+class B200AttnProcessor:
+    """diffusers AttnProcessor protocol (`attn.set_processor(p)`; `p(attn, hidden_states, encoder_hidden_states,
+    attention_mask, temb)`) with the hacked return contract of hacked_AttnProcessor2_0 (diffsim/hacked_attn.py:101):
+    (hidden_states, query, key, value, residual).  The scaled-dot-product attention runs in the sm_100a kernel."""
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, *args, **kwargs):
+        if attention_mask is not None:
+            raise NotImplementedError("attention masks are not used on the DiffSim path (hacked_attn.py:81-83 passes None)")
+        residual = hidden_states
+        if getattr(attn, "spatial_norm", None) is not None:
+            hidden_states = attn.spatial_norm(hidden_states, temb)
+        input_ndim = hidden_states.ndim
+        if input_ndim == 4:
+            batch_size, channel, height, width = hidden_states.shape
+            hidden_states = hidden_states.view(batch_size, channel, height * width).transpose(1, 2)
+        batch_size = hidden_states.shape[0]
+        query, key, value = project_qkv(attn, hidden_states, encoder_hidden_states)
+        out = ops.attn_fwd(query, key, value)                       # (B,H,S,D) view over (B,S,H*D)
+        head_dim = query.shape[-1]
+        hidden_states = out.transpose(1, 2).reshape(batch_size, -1, attn.heads * head_dim).to(query.dtype)
+        hidden_states = attn.to_out[0](hidden_states)
+        hidden_states = attn.to_out[1](hidden_states)
+        if input_ndim == 4:
+            hidden_states = hidden_states.transpose(-1, -2).reshape(batch_size, channel, height, width)
+        if getattr(attn, "residual_connection", False):
+            hidden_states = hidden_states + residual
+        hidden_states = hidden_states / getattr(attn, "rescale_output_factor", 1.0)
+        return hidden_states, query, key, value, residual

@@ -21,6 +21,14 @@ _DTYPES = {torch.float16: N.DS_F16, torch.bfloat16: N.DS_BF16, torch.float32: N.
 # per-device scratch buffers (grown on demand, reused across calls on the same stream)
 _workspaces: dict = {}
 
+# number of diffsim_b200 CUDA kernels launched through this module (bench.py reports it as gpu_launches)
+LAUNCHES = 0
+
+
+def _count(n: int) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
 
 def _mode(similarity) -> int:
     if isinstance(similarity, int):
@@ -106,6 +114,7 @@ def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: Optional[
     with torch.cuda.device(dev):
         N.check(lib.ds_attn_fwd(q4, k4, _t4(v), float(scale) if scale else 0.0, _t4(out), ws.data_ptr(), ws.numel(),
                                 _stream(dev)))
+    _count(2)  # meta + attention
     return out
 
 
@@ -127,6 +136,7 @@ def aas_groups(q: torch.Tensor, k_self: torch.Tensor, v_self: torch.Tensor, k: t
         N.check(lib.ds_aas_groups(q5, _t5(k_self), _t5(v_self), _t5(k), _t5(v), gq.data_ptr(), go.data_ptr(), n_groups,
                                   kv.data_ptr(), n_entries, float(scale) if scale else 0.0, _mode(similarity),
                                   dirs.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)))
+    _count(2)  # attention + finish
     return dirs
 
 
@@ -145,7 +155,33 @@ def aas_pairs(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, pair_idx, simil
     with torch.cuda.device(dev):
         N.check(lib.ds_aas_pairs(q5, _t5(k), _t5(v), pairs.data_ptr(), P, float(scale) if scale else 0.0,
                                  _mode(similarity), scores.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)))
+    _count(4)  # setup + attention + finish + pair combine
     return scores
+
+
+def aas_triplets(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, trip_idx, similarity="cosine",
+                 scale: Optional[float] = None, round_scores: bool = False, want_flags: bool = True):
+    """2AFC triplets (ref, left, right) as the benchmark drivers score them (cute_main.py:111-132,196-205):
+    returns (ab, ac, counts, flags) on the device: ab = diffsim(ref,left), ac = diffsim(ref,right) (float32 [T]),
+    counts int32[2] = {correct, correct_2x}, flags uint8[T].  One library call, no host sync."""
+    lib = N.load()
+    dev = _need_cuda(q, k, v)
+    trips = _i32(trip_idx, dev).reshape(-1, 3)
+    T = trips.shape[0]
+    ab = torch.empty(T, dtype=torch.float32, device=dev)
+    ac = torch.empty(T, dtype=torch.float32, device=dev)
+    counts = torch.empty(2, dtype=torch.int32, device=dev)
+    flags = torch.empty(T, dtype=torch.uint8, device=dev) if want_flags else None
+    q5 = _t5(q)
+    nbytes = lib.ds_aas_triplets_workspace_bytes(q5, T)
+    ws = _workspace(dev, nbytes)
+    with torch.cuda.device(dev):
+        N.check(lib.ds_aas_triplets(q5, _t5(k), _t5(v), trips.data_ptr(), T, float(scale) if scale else 0.0,
+                                    _mode(similarity), N.DS_OPT_ROUND_SCORES if round_scores else 0, ab.data_ptr(),
+                                    ac.data_ptr(), counts.data_ptr(), flags.data_ptr() if want_flags else None,
+                                    ws.data_ptr(), ws.numel(), _stream(dev)))
+    _count(4)  # setup + attention + finish + combine/decide
+    return ab, ac, counts, flags
 
 
 def aas_matrix(q: torch.Tensor, k_self: torch.Tensor, v_self: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
@@ -164,6 +200,7 @@ def aas_matrix(q: torch.Tensor, k_self: torch.Tensor, v_self: torch.Tensor, k: t
         N.check(lib.ds_aas_matrix(q5, _t5(k_self), _t5(v_self), k5, _t5(v), float(scale) if scale else 0.0,
                                   _mode(similarity), out.data_ptr(), out.stride(0), ws.data_ptr(), ws.numel(),
                                   _stream(dev)))
+    _count(3)  # setup + attention + finish
     return out
 
 
@@ -192,6 +229,7 @@ def pair_reduce(x: torch.Tensor, y: torch.Tensor, similarity="cosine") -> torch.
         N.check(lib.ds_pair_reduce(x2.data_ptr(), y2.data_ptr(), P, E, x2.stride(0) if P > 1 else E,
                                    y2.stride(0) if P > 1 else E, _dtype_code(x2), _mode(similarity), out.data_ptr(),
                                    ws.data_ptr(), ws.numel(), _stream(dev)))
+    _count(1)
     return out
 
 
@@ -219,6 +257,7 @@ def simmat(rows: torch.Tensor, cols: Optional[torch.Tensor] = None, similarity="
         N.check(lib.ds_simmat(rows.data_ptr(), nr, rows.stride(0), cols.data_ptr(), nc, cols.stride(0), L,
                               _dtype_code(rows), _mode(similarity), out.data_ptr(), out.stride(0), ws.data_ptr(),
                               ws.numel(), _stream(dev)))
+    _count(6)  # 2 statistics passes, 2 statistics finishes, GEMM, normalise
     return out
 
 
@@ -238,7 +277,21 @@ def twoafc(ab: torch.Tensor, ac: torch.Tensor, similarity="cosine") -> Tuple[tor
     with torch.cuda.device(dev):
         N.check(lib.ds_twoafc(ab.data_ptr(), ac.data_ptr(), n, _mode(similarity), counts.data_ptr(), flags.data_ptr(),
                               _stream(dev)))
+    _count(1)
     return counts, flags
+
+
+def profile_enable(on: bool = True) -> None:
+    N.check(N.load().ds_profile_enable(1 if on else 0))
+
+
+def profile_collect() -> Tuple[float, int]:
+    """(summed device milliseconds, launches) of the attention kernel since the last call."""
+    import ctypes as C
+
+    ms, n = C.c_float(0.0), C.c_int(0)
+    N.check(N.load().ds_profile_collect(C.byref(ms), C.byref(n)))
+    return float(ms.value), int(n.value)
 
 
 def default_scale(head_dim: int) -> float:

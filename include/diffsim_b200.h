@@ -74,6 +74,15 @@ const char* ds_last_error(void);
 /* Device check: DS_OK iff the current device is compute capability 10.x. */
 int         ds_device_ok(void);
 
+/*
+ * Optional in-stream timing of the dominant kernel (the fused attention): when enabled, every
+ * attention launch is bracketed by cudaEventRecord on the caller's stream (up to 256 launches are
+ * kept).  ds_profile_collect waits for the recorded launches, returns their summed device time and
+ * count, and resets the ring.  Used by bench.py for the roofline figure; off by default.
+ */
+int ds_profile_enable(int on);
+int ds_profile_collect(float* total_ms, int* launches);
+
 /* ---- K1: attention ------------------------------------------------------ */
 
 /*
@@ -125,6 +134,26 @@ int ds_aas_pairs(ds_tensor5 q, ds_tensor5 k, ds_tensor5 v,
                  float scale, int mode, float* scores,
                  void* ws, size_t ws_bytes, void* stream);
 size_t ds_aas_pairs_workspace_bytes(ds_tensor5 q, int64_t n_pairs);
+
+/*
+ * 2AFC triplets as the benchmark drivers score them (cute_main.py:111-132,196-205;
+ * night_main.py:157-163): for trip_idx[t] = (ref, left, right)
+ *     ab[t] = DiffSim.diffsim(ref, left),  ac[t] = DiffSim.diffsim(ref, right)
+ * plus the decision counts of ds_twoafc.  The reference image's queries and self
+ * attention are shared by both pairs (7 attentions per triplet instead of the
+ * reference's 8; the reference recomputes image A, cute_main.py:111-132).
+ * flags_out (optional): uint8[n] per-triplet "correct".  counts: int32[2].
+ * opts: DS_OPT_ROUND_SCORES rounds every directional similarity and the pair
+ * score to the input dtype before comparing, emulating the dtype of the
+ * reference's score tensors (diffsim/diffsim.py:187-197 return fp16/bf16).
+ */
+#define DS_OPT_ROUND_SCORES 1
+int ds_aas_triplets(ds_tensor5 q, ds_tensor5 k, ds_tensor5 v,
+                    const int32_t* trip_idx, int64_t n_triplets,
+                    float scale, int mode, int opts,
+                    float* ab, float* ac, int32_t* counts, uint8_t* flags_out,
+                    void* ws, size_t ws_bytes, void* stream);
+size_t ds_aas_triplets_workspace_bytes(ds_tensor5 q, int64_t n_triplets);
 
 /*
  * Directional score matrix for retrieval (the reference only

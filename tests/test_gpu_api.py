@@ -1,0 +1,134 @@
+"""The reference-facing Python surface on the GPU: scorer classes, capture hooks / processor, host-buffer scorer."""
+import pytest
+import torch
+
+from oracle import aas_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return "cuda"
+
+
+def test_diffsim_class_returns_reference_dtype_and_shape():
+    dev = _cuda()
+    from diffsim_b200.diffsim import DiffSim, SyntheticTrunk, diffsim_DiT, diffsim_xl
+
+    ds = DiffSim(torch.float16, dev, trunk=SyntheticTrunk((2, 8, 256, 160), torch.float16, dev))
+    kw = dict(img_size=512, prompt="p", target_block="up_blocks", target_layer=[0], target_step=600, seed=2334, device=dev)
+    s = ds.diffsim("cat@1.0", "cat@0.8", similarity="cosine", **kw)
+    assert s.dtype == torch.float16 and s.shape == (1,)             # diffsim/diffsim.py:197 (cosine keeps a dim)
+    m = ds.diffsim("cat@1.0", "cat@0.8", similarity="mse", **kw)
+    assert m.dtype == torch.float16 and m.shape == ()
+    A = ds.diffsim_value("cat@1.0", **kw)
+    Bm = ds.diffsim_value("cat@0.8", **kw)
+    assert A[0].shape == (2, 8, 256, 160) and A[0].stride() == (327680, 160, 1280, 1)
+    ref = O.aas_pair_score(*[t.cpu() for t in A], *[t.cpu() for t in Bm])
+    assert float(s) == pytest.approx(ref, rel=2e-3)                  # fp16 quantisation of the returned score
+    assert float(ds.diffsim("cat@1.0", "cat@1.0", similarity="cosine", **kw)) == 1.0
+    # the drivers' comparison works on the returned tensors (cute_main.py:196-205)
+    far = ds.diffsim("cat@1.0", "dog@1.0", similarity="cosine", **kw)
+    assert bool(s > far)
+    # fp32 scores on request
+    ds32 = DiffSim(torch.float16, dev, trunk=ds.trunk, match_reference_dtype=False)
+    s32 = ds32.diffsim("cat@1.0", "cat@0.8", similarity="cosine", **kw)
+    assert s32.dtype == torch.float32 and float(s32) == pytest.approx(ref, rel=1e-3)
+    # DiT: packed-qkv views are consumed in place
+    dit = diffsim_DiT(256, 600, dev)
+    d = dit.diffsim_score("cat@1.0", "cat@0.9", 256, "p", "up_blocks", [14], 600, "cosine", 2334)
+    A, Bm = dit.trunk.extract("cat@1.0", target_step=600), dit.trunk.extract("cat@0.9", target_step=600)
+    assert A[0].stride()[2] == 3 * 16 * 72
+    assert float(d) == pytest.approx(O.aas_pair_score(*[t.cpu() for t in A], *[t.cpu() for t in Bm]), rel=2e-3)
+    xl = diffsim_xl(torch.float16, dev)
+    x = xl.diffsim_score("cat@1.0", "cat@0.9", 1024, "p", "up_blocks", [0, 1, 2], 600, "cosine", 2334)
+    assert x.shape == (1,) and 0 < float(x) <= 1
+
+
+class _FakeAttention(torch.nn.Module):
+    """Shape of diffusers.models.attention_processor.Attention as far as the processors use it."""
+
+    def __init__(self, dim, heads, dtype, dev):
+        super().__init__()
+        self.heads = heads
+        self.to_q = torch.nn.Linear(dim, dim, bias=False, dtype=dtype, device=dev)
+        self.to_k = torch.nn.Linear(dim, dim, bias=False, dtype=dtype, device=dev)
+        self.to_v = torch.nn.Linear(dim, dim, bias=False, dtype=dtype, device=dev)
+        self.to_out = torch.nn.ModuleList([torch.nn.Linear(dim, dim, dtype=dtype, device=dev), torch.nn.Dropout(0.0)])
+        self.spatial_norm = self.group_norm = None
+        self.norm_cross = False
+        self.residual_connection = False
+        self.rescale_output_factor = 1.0
+        self.processor = None
+
+    def forward(self, hidden_states):
+        return self.processor(self, hidden_states)[0] if self.processor else hidden_states
+
+
+def test_hooks_and_processor_follow_the_reference_contract():
+    dev = _cuda()
+    import torch.nn.functional as F
+
+    from diffsim_b200 import hooks
+
+    torch.manual_seed(0)
+    attn = _FakeAttention(1280, 8, torch.float16, dev)
+    x = torch.randn(2, 256, 1280, device=dev, dtype=torch.float16)
+    # protocol 2: forward-pre-hook leaves module.stores = [q, k, v]
+    with hooks.capture(attn, hooks.make_sd_pre_hook()):
+        attn(x)
+    q, k, v = attn.stores
+    assert q.shape == (2, 8, 256, 160) and q.stride() == (327680, 160, 1280, 1)
+    assert torch.equal(q, attn.to_q(x).view(2, 256, 8, 160).transpose(1, 2))
+    assert len(attn._forward_pre_hooks) == 0                      # removed (the reference accumulates them)
+    with hooks.capture(attn, hooks.make_sd_pre_hook(early_exit=True)):
+        with pytest.raises(hooks.StopForward):
+            attn(x)
+    # protocol 1: processor returning (hidden_states, q, k, v, residual) -- hacked_attn.py:101
+    out, q2, k2, v2, res = hooks.B200AttnProcessor()(attn, x)
+    assert torch.equal(q2, q) and res is x
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(2, 256, 1280)
+    ref = attn.to_out[0](ref)
+    assert (out.float() - ref.float()).abs().max().item() < 2e-2
+
+    class _FakeTimmAttention(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.num_heads, self.head_dim = 16, 72
+            self.qkv = torch.nn.Linear(1152, 3 * 1152, dtype=torch.float16, device=dev)
+            self.q_norm = self.k_norm = torch.nn.Identity()
+
+        def forward(self, x):
+            return x
+
+    t = _FakeTimmAttention()
+    xt = torch.randn(2, 256, 1152, device=dev, dtype=torch.float16)
+    with hooks.capture(t, hooks.make_dit_pre_hook()):
+        t(xt)
+    q, k, v = t.stores
+    assert q.shape == (2, 16, 256, 72) and q.stride() == (256 * 3 * 1152, 72, 3 * 1152, 1)
+    from diffsim_b200 import ops
+
+    o = ops.attn_fwd(q, k, v)
+    assert (o.float() - F.scaled_dot_product_attention(q, k, v).float()).abs().max().item() < 4e-3
+
+
+def test_host_scorer_equals_device_scorer():
+    dev = _cuda()
+    from diffsim_b200 import scoring, synth
+
+    shape = (2, 4, 128, 64)
+    T = 50
+    q, k, v = synth.device_cache(*shape, 3 * T, torch.float16, dev, seed=3)
+    cache = scoring.QKVCache(q, k, v)
+    trips = torch.arange(3 * T, dtype=torch.int32, device=dev).view(T, 3)
+    _, _, counts, _ = scoring.score_triplets(cache, trips, "cosine")
+    host = scoring.QKVCache.empty(3 * T, *shape, torch.float16, "cpu", pin=True)
+    for hm, dm in zip(host.memory(), cache.memory()):
+        hm.copy_(dm)
+    scorer = scoring.HostTripletScorer(shape, torch.float16, dev, chunk_triplets=16)   # 4 chunks, ragged tail
+    got = scorer.score(host, T)
+    assert got == (int(counts[0]), int(counts[1]))
+    assert scorer.h2d_bytes == 3 * T * cache.bytes_per_image and scorer.d2h_bytes == 8
