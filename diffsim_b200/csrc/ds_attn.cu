@@ -2,20 +2,31 @@
 //
 // One persistent, warp-specialised CTA per SM:
 //
-//   warp 0        TMA producer   Q tile (per stream) and a ring of 64-row K / V blocks
-//   warp 1        MMA issuer     tcgen05.mma: S = Q K^T (fp32, TMEM), O = P V (fp32, TMEM)
+//   warp 0        TMA producer   Q tile (per stream) and a ring of 64-row K / V stages
+//   warp 1        MMA issuer     tcgen05.mma: S = Q K^T (fp32, TMEM), O (+)= P V (fp32, TMEM)
 //   warp 2        TMEM allocator
-//   warps 4-11    softmax        2 warpgroups x 128 threads; thread = one row, half the kv columns;
+//   warps 4-11    softmax        256 threads; thread = (q row, 64 of the 128 kv columns of an S half);
 //                                S (TMEM) -> exp2 -> P (16-bit, 128B-swizzled smem, the A operand of PV)
-//   warps 12-15   epilogue       O (TMEM) -> 1/l -> round to input dtype ->
-//                                  self item : keep O_self on chip (smem), accumulate |O_self|^2
-//                                  cross item: dot(O_cross,O_self), |O_cross|^2, sum (O_cross-O_self)^2
+//   warps 12-15   epilogue       O (TMEM) -> 1/l ->
+//                                  self item : O_self rounded to the input dtype, kept on chip (TMEM), |O_self|^2
+//                                  cross item: dot(O_cross,O_self), |O_cross|^2 or sum (O_cross-O_self)^2
 //                                  store mode: write O to global (the SDPA replacement)
+//                                and, for kv lengths > 256, the online-softmax rescale of O between groups
 //
-// A "stream" is (group, b, h, 128-row q tile).  The Q tile stays resident while the kv images of the
-// group stream through; the first item of a group is the query image's own K/V (the self attention
-// of diffsim/diffsim.py:179-180), whose output never leaves the SM.  The MMA warp issues
-// QK(n+1) before PV(n) so that the tensor pipe works on PV(n) while the softmax warps chew on S(n+1).
+// Work decomposition.  A "stream" is (group, b, h, 128-row q tile): the Q tile stays resident while the kv
+// images of the group ("items") stream through; the first item of a group is the query image's own K/V (the
+// self attention of diffsim/diffsim.py:179-180), whose output never leaves the SM.  An item is cut into kv
+// GROUPS of 256 rows, a group into two HALVES (A, B) of 128 rows with their own S columns in TMEM and their
+// own P buffer in shared memory, a half into 64-row ring stages.
+//
+// Softmax.  The row maximum is taken over the whole group before any exponential (exact two-pass softmax:
+// for kv <= 256 -- SD-1.5 up_blocks[0], DiT -- there is exactly one group and no rescaling anywhere); across
+// groups the running maximum / sum are carried in registers and O is rescaled in TMEM by the epilogue warps
+// (skipped per warp when no row maximum moved).
+//
+// Pipeline.  The MMA warp issues, in this fixed order, QK_A(u+1), PV_A(u), QK_B(u+1), PV_B(u): as soon as the
+// softmax warps have turned half A of group u into P_A they start on half B while the tensor core already
+// recomputes S_A for the next group and consumes P_A.  The TMA producer feeds the ring in the same order.
 //
 // Replaces diffsim/diffsim.py:177-197 (diffsim_xl.py:135-155, diffsim_dit.py:130-142).
 // Algorithmic work per directional attention: 4*B*H*Sq*Skv*D flops.
@@ -24,17 +35,21 @@
 
 namespace ds {
 
-enum : int { ATTN_MODE_AAS = 0, ATTN_MODE_STORE = 1 };
+enum : int { ATTN_MODE_COS = 0, ATTN_MODE_MSE = 1, ATTN_MODE_STORE = 2 };
 
 constexpr int kAttnThreads = 512;
-constexpr int kBlockQ = 128;    // q rows per tile == TMEM lanes
-constexpr int kBlockKV = 64;    // kv rows per ring stage
-constexpr int kMaxKV = 256;     // single-pass softmax: the whole score row lives in TMEM
+constexpr int kBlockQ = 128;     // q rows per tile == TMEM lanes
+constexpr int kStageKV = 64;     // kv rows per ring stage
+constexpr int kHalfKV = 128;     // kv rows per S half
+constexpr int kGroupKV = 256;    // kv rows per softmax group (two halves)
 constexpr int kTmemCols = 512;
-constexpr int kTmemS = 0;       // S: columns [0, 256)
-constexpr int kTmemO = 256;     // O: columns [256, 256 + D_PAD)
-constexpr int kTmemSum = 480;   // row sums: columns 480 + 2*parity + warpgroup
-constexpr int kPBytes = kBlockQ * kMaxKV * 2;  // 64 KB, four [128 x 64] 128B-swizzled sub-tiles
+constexpr int kTmemS = 0;        // S_A: columns [0,128), S_B: [128,256)
+constexpr int kTmemO = 256;      // O: [256, 256 + D_PAD)
+constexpr int kTmemOs = 416;     // O_self, packed 16-bit: [416, 416 + D_PAD/2)
+constexpr int kTmemSum = 496;    // row sums: 496 + 2 * (item parity) + (column half of the thread)
+constexpr int kTmemAlpha = 500;  // online-softmax rescale factors: 500 + (correction parity)
+constexpr int kPSubBytes = kBlockQ * 128;       // one [128 x 64] 128B-swizzled P sub-tile: 16 KB
+constexpr int kPBytes = 4 * kPSubBytes;         // P_A (sub-tiles 0,1) and P_B (2,3): 64 KB
 
 template <int D>
 struct AttnCfg {
@@ -46,16 +61,16 @@ struct AttnCfg {
   static constexpr int CPS = SUBW / 16;                           // 16-element K chunks per sub-tile
   static constexpr int Q_SUB_BYTES = kBlockQ * SUB_BYTES;
   static constexpr int Q_BYTES = NSUB * Q_SUB_BYTES;
-  static constexpr int KV_SUB_BYTES = kBlockKV * SUB_BYTES;
+  static constexpr int KV_SUB_BYTES = kStageKV * SUB_BYTES;
   static constexpr int STAGE_BYTES = NSUB * KV_SUB_BYTES;
-  static constexpr int OS_BYTES = kBlockQ * D_PAD * 2;            // [D_PAD/8][128 rows][16 B]
   static constexpr int MISC_BYTES = 2048 /*max exchange*/ + 128 /*epilogue reduce*/ + 512 /*barriers*/;
   static constexpr int kMaxSmem = 232448;
-  static constexpr int STAGES_RAW = (kMaxSmem - Q_BYTES - OS_BYTES - kPBytes - MISC_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = Q_BYTES + OS_BYTES + kPBytes + STAGES * STAGE_BYTES + MISC_BYTES;
-  static_assert(STAGES >= 3, "not enough shared memory for the K/V ring");
-  static_assert(kTmemO + D_PAD <= kTmemSum, "TMEM budget");
+  static constexpr int STAGES_RAW = (kMaxSmem - Q_BYTES - kPBytes - MISC_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 12 ? 12 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = Q_BYTES + kPBytes + STAGES * STAGE_BYTES + MISC_BYTES;
+  static_assert(STAGES >= 4, "not enough shared memory for the K/V ring");
+  static_assert(kTmemO + D_PAD <= kTmemOs && kTmemOs + D_PAD / 2 <= kTmemSum, "TMEM budget");
+  static_assert(Q_BYTES % 1024 == 0 && STAGE_BYTES % 1024 == 0, "swizzle atoms need 1024-byte aligned tiles");
 };
 
 struct AttnParams {
@@ -65,10 +80,8 @@ struct AttnParams {
   const int32_t* kv_idx;     // [n_entries] kv image of each entry
   int n_groups;
   int self_first;            // 1: every group starts with the query image's own K/V (AAS)
-  int mode;                  // ATTN_MODE_AAS | ATTN_MODE_STORE
   int B, H, Sq, Skv;
   int n_qt;                  // q tiles per (b,h)
-  int n_kb;                  // 64-row kv blocks per item
   float scale_log2;          // softmax scale * log2(e)
   // AAS output: part[entry][bh * n_qt + qt] = (dot, |Oc|^2, |Os|^2, sum (Oc-Os)^2)
   float4* part;
@@ -77,7 +90,51 @@ struct AttnParams {
   int64_t out_sb, out_sh, out_ss;
 };
 
-template <int D, bool kBf16>
+// One kv group of one item of one stream, as every warp role enumerates them (identically).
+struct GroupInfo {
+  int b, h, qt, bh, qi;     // stream
+  int img, entry;           // item: kv image, index into kv_idx / part (cross items)
+  int kv0, rowsA, rowsB;    // group: first kv row, valid rows of the two halves
+  bool self, first_of_stream, last_of_stream, first_of_item, last_of_item;
+};
+
+template <typename F>
+__device__ __forceinline__ void for_each_group(const AttnParams& p, F&& f) {
+  const int BH = p.B * p.H;
+  const int64_t n_streams = (int64_t)p.n_groups * BH * p.n_qt;
+  const int n_grp = (p.Skv + kGroupKV - 1) / kGroupKV;
+  // stream -> (bh, group, q tile): q tile fastest so that neighbouring CTAs share K/V in L2
+  for (int64_t st = blockIdx.x; st < n_streams; st += gridDim.x) {
+    GroupInfo G;
+    G.qt = (int)(st % p.n_qt);
+    const int64_t r = st / p.n_qt;
+    const int g = (int)(r % p.n_groups);
+    G.bh = (int)(r / p.n_groups);
+    G.b = G.bh / p.H;
+    G.h = G.bh % p.H;
+    G.qi = p.group_q[g];
+    const int t0 = p.group_off[g], t1 = p.group_off[g + 1];
+    const int n_items = (t1 - t0) + p.self_first;
+    for (int it = 0; it < n_items; ++it) {
+      G.self = p.self_first && it == 0;
+      G.entry = t0 + it - p.self_first;
+      G.img = G.self ? G.qi : p.kv_idx[G.entry];
+      for (int gg = 0; gg < n_grp; ++gg) {
+        G.kv0 = gg * kGroupKV;
+        const int rem = p.Skv - G.kv0;
+        G.rowsA = min(rem, kHalfKV);
+        G.rowsB = max(0, min(rem - kHalfKV, kHalfKV));
+        G.first_of_item = gg == 0;
+        G.last_of_item = gg == n_grp - 1;
+        G.first_of_stream = it == 0 && gg == 0;
+        G.last_of_stream = it == n_items - 1 && gg == n_grp - 1;
+        f(G);
+      }
+    }
+  }
+}
+
+template <int D, bool kBf16, int MODE>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_ks,
                 const __grid_constant__ CUtensorMap map_vs, const __grid_constant__ CUtensorMap map_k,
@@ -87,20 +144,23 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   uint8_t* sQ = smem;
   uint8_t* sP = sQ + C::Q_BYTES;
   uint8_t* sRing = sP + kPBytes;
-  uint8_t* sOs = sRing + C::STAGES * C::STAGE_BYTES;
-  float* sMax = reinterpret_cast<float*>(sOs + C::OS_BYTES);       // [2 parity][2 wg][128]
-  float* sRed = sMax + 512;                                        // [2 parity][4 warps][4]
+  float* sMax = reinterpret_cast<float*>(sRing + C::STAGES * C::STAGE_BYTES);  // [2 parity][2 col half][128]
+  float* sRed = sMax + 512;                                                    // [2 parity][4 warps][4]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 32);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
-  uint64_t* s_full = bars + 2;
-  uint64_t* s_empty = bars + 3;
-  uint64_t* p_full = bars + 4;
-  uint64_t* pv_done = bars + 5;
-  uint64_t* o_empty = bars + 6;
-  uint64_t* kv_full = bars + 8;
-  uint64_t* kv_empty = bars + 8 + C::STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * C::STAGES);
+  uint64_t* s_full = bars + 2;      // [2] S half written by the tensor core
+  uint64_t* s_empty = bars + 4;     // [2] S half consumed by the softmax warps
+  uint64_t* p_full = bars + 6;      // [2] P half written by the softmax warps
+  uint64_t* pv_done = bars + 8;     // [2] P half consumed by the tensor core
+  uint64_t* o_full = bars + 10;     // all PV of an item done
+  uint64_t* o_empty = bars + 11;    // O read out by the epilogue warps
+  uint64_t* alpha_full = bars + 12; // online softmax: rescale factors of a group published
+  uint64_t* corr_done = bars + 13;  // online softmax: O rescaled
+  uint64_t* kv_full = bars + 16;
+  uint64_t* kv_empty = bars + 16 + C::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16 + 2 * C::STAGES);
+  static_assert((16 + 2 * C::STAGES) * 8 + 16 <= 512, "barrier area");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -118,11 +178,16 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
-    mbar_init(s_full, 1);
-    mbar_init(s_empty, 256);
-    mbar_init(p_full, 256);
-    mbar_init(pv_done, 1);
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(&s_full[h], 1);
+      mbar_init(&s_empty[h], 256);
+      mbar_init(&p_full[h], 256);
+      mbar_init(&pv_done[h], 1);
+    }
+    mbar_init(o_full, 1);
     mbar_init(o_empty, 128);
+    mbar_init(alpha_full, 128);
+    mbar_init(corr_done, 128);
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
@@ -138,353 +203,479 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int BH = p.B * p.H;
-  const int64_t n_streams = (int64_t)p.n_groups * BH * p.n_qt;
-  const int n_kb = p.n_kb;
-
-  // stream -> (bh, group, q tile): q tile fastest so that neighbouring CTAs share K/V in L2
-#define DS_DECODE_STREAM(st)                                   \
-  const int qt = (int)((st) % p.n_qt);                         \
-  const int64_t _r = (st) / p.n_qt;                            \
-  const int g = (int)(_r % p.n_groups);                        \
-  const int bh = (int)(_r / p.n_groups);                       \
-  const int b = bh / p.H, h = bh % p.H;                        \
-  const int t0 = p.group_off[g], t1 = p.group_off[g + 1];      \
-  const int n_items = (t1 - t0) + p.self_first;                \
-  (void)b; (void)h; (void)qt;
-
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       int stage = 0;
-      uint32_t phase = 0;
-      uint32_t gi = 0;
-      bool have_prev = false;
-      int prev_img = 0, prev_b = 0, prev_h = 0;
-      bool prev_self = false;
-      auto load_block = [&](const CUtensorMap* m, int img, int bb, int hh, int j) {
-        mbar_wait(&kv_empty[stage], phase ^ 1);
-        uint8_t* dst = sRing + (size_t)stage * C::STAGE_BYTES;
-        mbar_arrive_expect_tx(&kv_full[stage], C::STAGE_BYTES);
+      uint32_t phase = 0, sc = 0;
+      auto load_rows = [&](const CUtensorMap* m, int img, int bb, int hh, int row0, int rows) {
+        for (int r = 0; r < rows; r += kStageKV) {
+          mbar_wait(&kv_empty[stage], phase ^ 1);
+          uint8_t* dst = sRing + (size_t)stage * C::STAGE_BYTES;
+          mbar_arrive_expect_tx(&kv_full[stage], C::STAGE_BYTES);
 #pragma unroll
-        for (int s = 0; s < C::NSUB; ++s)
-          tma_load_5d(dst + s * C::KV_SUB_BYTES, m, &kv_full[stage], s * C::SUBW, j * kBlockKV, hh, bb, img);
-        if (++stage == C::STAGES) {
-          stage = 0;
-          phase ^= 1;
+          for (int s = 0; s < C::NSUB; ++s)
+            tma_load_5d(dst + s * C::KV_SUB_BYTES, m, &kv_full[stage], s * C::SUBW, row0 + r, hh, bb, img);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       };
-      for (int64_t st = blockIdx.x; st < n_streams; st += gridDim.x, ++gi) {
-        DS_DECODE_STREAM(st);
-        const int qi = p.group_q[g];
-        // Q tile
-        mbar_wait(q_empty, (gi & 1) ^ 1);
-        mbar_arrive_expect_tx(q_full, C::Q_BYTES);
+      GroupInfo prev = {};
+      bool have_prev = false;
+      for_each_group(p, [&](const GroupInfo& G) {
+        if (G.first_of_stream) {
+          mbar_wait(q_empty, (sc & 1) ^ 1);
+          mbar_arrive_expect_tx(q_full, C::Q_BYTES);
 #pragma unroll
-        for (int s = 0; s < C::NSUB; ++s)
-          tma_load_5d(sQ + s * C::Q_SUB_BYTES, &map_q, q_full, s * C::SUBW, qt * kBlockQ, h, b, qi);
-        for (int it = 0; it < n_items; ++it) {
-          const bool self = p.self_first && it == 0;
-          const int img = self ? qi : p.kv_idx[t0 + it - p.self_first];
-          // K blocks of this item
-          for (int j = 0; j < n_kb; ++j) load_block(self ? &map_ks : &map_k, img, b, h, j);
-          // V blocks of the previous item (the MMA warp issues QK(n+1) before PV(n))
-          if (have_prev)
-            for (int j = 0; j < n_kb; ++j) load_block(prev_self ? &map_vs : &map_v, prev_img, prev_b, prev_h, j);
-          have_prev = true;
-          prev_img = img;
-          prev_b = b;
-          prev_h = h;
-          prev_self = self;
+          for (int s = 0; s < C::NSUB; ++s)
+            tma_load_5d(sQ + s * C::Q_SUB_BYTES, &map_q, q_full, s * C::SUBW, G.qt * kBlockQ, G.h, G.b, G.qi);
+          ++sc;
         }
+        // the order the MMA warp consumes the ring in: K_A(u), V_A(u-1), K_B(u), V_B(u-1)
+        load_rows(G.self ? &map_ks : &map_k, G.img, G.b, G.h, G.kv0, G.rowsA);
+        if (have_prev) load_rows(prev.self ? &map_vs : &map_v, prev.img, prev.b, prev.h, prev.kv0, prev.rowsA);
+        if (G.rowsB) load_rows(G.self ? &map_ks : &map_k, G.img, G.b, G.h, G.kv0 + kHalfKV, G.rowsB);
+        if (have_prev && prev.rowsB)
+          load_rows(prev.self ? &map_vs : &map_v, prev.img, prev.b, prev.h, prev.kv0 + kHalfKV, prev.rowsB);
+        prev = G;
+        have_prev = true;
+      });
+      if (have_prev) {
+        load_rows(prev.self ? &map_vs : &map_v, prev.img, prev.b, prev.h, prev.kv0, prev.rowsA);
+        if (prev.rowsB) load_rows(prev.self ? &map_vs : &map_v, prev.img, prev.b, prev.h, prev.kv0 + kHalfKV, prev.rowsB);
       }
-      if (have_prev)
-        for (int j = 0; j < n_kb; ++j) load_block(prev_self ? &map_vs : &map_v, prev_img, prev_b, prev_h, j);
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
       const uint32_t fmt = kBf16 ? 1u : 0u;
-      const uint32_t idesc_qk = umma_idesc_f16(fmt, kBlockQ, kBlockKV, 0, 0);
+      const uint32_t idesc_qk = umma_idesc_f16(fmt, kBlockQ, kStageKV, 0, 0);
       const uint32_t idesc_pv = umma_idesc_f16(fmt, kBlockQ, C::D_PAD, 0, 1);
-      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP), ring_addr = smem_u32(sRing);
       constexpr uint32_t SBO = 8 * C::SUB_BYTES;  // eight swizzle rows
+      // descriptors of the buffer bases; tiles are addressed by adding (byte offset >> 4) to the low word
+      const uint64_t q_desc0 = umma_smem_desc(smem_u32(sQ), 16, SBO, C::LAYOUT);
+      const uint64_t k_desc0 = umma_smem_desc(smem_u32(sRing), 16, SBO, C::LAYOUT);
+      const uint64_t v_desc0 = umma_smem_desc(smem_u32(sRing), C::KV_SUB_BYTES, SBO, C::LAYOUT);
+      const uint64_t p_desc0 = umma_smem_desc(smem_u32(sP), 16, 1024, UMMA_SW128);
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t n = 0;   // items issued by this CTA
-      uint32_t gi = 0;
+      uint32_t qk_cnt[2] = {0, 0}, pv_cnt[2] = {0, 0}, sc = 0, items_pv = 0, corr = 0;
       auto advance = [&]() {
         if (++stage == C::STAGES) {
           stage = 0;
           phase ^= 1;
         }
       };
-      auto issue_pv = [&](uint32_t m) {
-        mbar_wait(p_full, m & 1);
-        mbar_wait(o_empty, (m & 1) ^ 1);
+      auto issue_qk = [&](const GroupInfo& G, int h) {
+        const int rows = h ? G.rowsB : G.rowsA;
+        mbar_wait(&s_empty[h], (qk_cnt[h] & 1) ^ 1);
+        if (h == 0 && G.first_of_stream) {
+          mbar_wait(q_full, sc & 1);
+          ++sc;
+        }
         tc_fence_after_sync();
-        for (int j = 0; j < n_kb; ++j) {
+        for (int r = 0, s = 0; r < rows; r += kStageKV, ++s) {
           mbar_wait(&kv_full[stage], phase);
           tc_fence_after_sync();
-          const uint32_t v_addr = ring_addr + stage * C::STAGE_BYTES;
+          const uint64_t k_desc = k_desc0 + (uint64_t)((stage * C::STAGE_BYTES) >> 4);
+          const uint32_t d_tmem = tmem_base + kTmemS + h * kHalfKV + s * kStageKV;
 #pragma unroll
-          for (int kk = 0; kk < kBlockKV / 16; ++kk) {
-            // A = P[:, 64 j + 16 kk ...] (K-major, 128B swizzle); B = V rows 16 kk.. (MN-major)
-            const uint64_t a_desc = umma_smem_desc(p_addr + j * (kBlockQ * 128) + kk * 32, 16, 1024, UMMA_SW128);
-            const uint64_t b_desc =
-                umma_smem_desc(v_addr + kk * 16 * C::SUB_BYTES, C::KV_SUB_BYTES, SBO, C::LAYOUT);
-            umma_f16_ss(tmem_base + kTmemO, a_desc, b_desc, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+          for (int kc = 0; kc < C::D_PAD / 16; ++kc) {
+            const int sub = kc / C::CPS, off = (kc % C::CPS) * 32;
+            umma_f16_ss(d_tmem, q_desc0 + (uint64_t)((sub * C::Q_SUB_BYTES + off) >> 4),
+                        k_desc + (uint64_t)((sub * C::KV_SUB_BYTES + off) >> 4), idesc_qk, kc > 0 ? 1u : 0u);
           }
           umma_commit(&kv_empty[stage]);
           advance();
         }
-        umma_commit(pv_done);
+        umma_commit(&s_full[h]);
+        ++qk_cnt[h];
+        if (G.last_of_stream && (h == 1 || G.rowsB == 0)) umma_commit(q_empty);
       };
-      for (int64_t st = blockIdx.x; st < n_streams; st += gridDim.x, ++gi) {
-        DS_DECODE_STREAM(st);
-        mbar_wait(q_full, gi & 1);
-        for (int it = 0; it < n_items; ++it, ++n) {
-          // S(n) = Q K^T, one N=64 slice per kv block
-          mbar_wait(s_empty, (n & 1) ^ 1);
-          tc_fence_after_sync();
-          for (int j = 0; j < n_kb; ++j) {
-            mbar_wait(&kv_full[stage], phase);
-            tc_fence_after_sync();
-            const uint32_t k_addr = ring_addr + stage * C::STAGE_BYTES;
-#pragma unroll
-            for (int kc = 0; kc < C::D_PAD / 16; ++kc) {
-              const int sub = kc / C::CPS, off = (kc % C::CPS) * 32;
-              const uint64_t a_desc = umma_smem_desc(q_addr + sub * C::Q_SUB_BYTES + off, 16, SBO, C::LAYOUT);
-              const uint64_t b_desc = umma_smem_desc(k_addr + sub * C::KV_SUB_BYTES + off, 16, SBO, C::LAYOUT);
-              umma_f16_ss(tmem_base + kTmemS + j * kBlockKV, a_desc, b_desc, idesc_qk, kc > 0 ? 1u : 0u);
-            }
-            umma_commit(&kv_empty[stage]);
-            advance();
+      auto issue_pv = [&](const GroupInfo& G, int h) {
+        const int rows = h ? G.rowsB : G.rowsA;
+        mbar_wait(&p_full[h], pv_cnt[h] & 1);
+        if (h == 0) {
+          if (G.first_of_item) {
+            mbar_wait(o_empty, (items_pv & 1) ^ 1);
+          } else {
+            mbar_wait(corr_done, corr & 1);
+            ++corr;
           }
-          if (it == n_items - 1) umma_commit(q_empty);
-          umma_commit(s_full);
-          if (n >= 1) issue_pv(n - 1);
         }
+        tc_fence_after_sync();
+        for (int r = 0, s = 0; r < rows; r += kStageKV, ++s) {
+          mbar_wait(&kv_full[stage], phase);
+          tc_fence_after_sync();
+          const uint64_t v_desc = v_desc0 + (uint64_t)((stage * C::STAGE_BYTES) >> 4);
+          const uint64_t p_desc = p_desc0 + (uint64_t)(((h * 2 + s) * kPSubBytes) >> 4);
+#pragma unroll
+          for (int kk = 0; kk < kStageKV / 16; ++kk) {
+            // A = P[:, 16 kk ...] of this sub-tile (K-major, 128B swizzle); B = V rows 16 kk.. (MN-major)
+            const uint32_t acc = (G.first_of_item && h == 0 && s == 0 && kk == 0) ? 0u : 1u;
+            umma_f16_ss(tmem_base + kTmemO, p_desc + (uint64_t)((kk * 32) >> 4),
+                        v_desc + (uint64_t)((kk * 16 * C::SUB_BYTES) >> 4), idesc_pv, acc);
+          }
+          umma_commit(&kv_empty[stage]);
+          advance();
+        }
+        umma_commit(&pv_done[h]);
+        ++pv_cnt[h];
+        if (G.last_of_item && (h == 1 || G.rowsB == 0)) {
+          umma_commit(o_full);
+          ++items_pv;
+        }
+      };
+      GroupInfo prev = {};
+      bool have_prev = false;
+      for_each_group(p, [&](const GroupInfo& G) {
+        issue_qk(G, 0);
+        if (have_prev) issue_pv(prev, 0);
+        if (G.rowsB) issue_qk(G, 1);
+        if (have_prev && prev.rowsB) issue_pv(prev, 1);
+        prev = G;
+        have_prev = true;
+      });
+      if (have_prev) {
+        issue_pv(prev, 0);
+        if (prev.rowsB) issue_pv(prev, 1);
       }
-      if (n >= 1) issue_pv(n - 1);
     }
   } else if (warp >= 4 && warp < 12) {
     // ------------------------------------------------------------------ softmax
-    const int wg = (warp - 4) >> 2;              // which half of the kv columns
+    const int wg = (warp - 4) >> 2;              // which 64 columns of each S half
     const int quad = warp & 3;                   // TMEM lane quadrant this warp may touch
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    const int col0 = wg * 128;
-    const int nvalid = max(0, min(128, p.Skv - col0));  // valid kv columns in this half
-    const uint32_t p_row = smem_u32(sP) + row * 128;
-    uint32_t n = 0;
-    for (int64_t st = blockIdx.x; st < n_streams; st += gridDim.x) {
-      DS_DECODE_STREAM(st);
-      for (int it = 0; it < n_items; ++it, ++n) {
-        const uint32_t par = n & 1;
-        mbar_wait(s_full, par);
+    const uint32_t s_col = tmem_base + lane_addr + kTmemS + wg * kStageKV;       // + h * 128 + c * 32
+    const uint32_t p_row = smem_u32(sP) + wg * kPSubBytes + row * 128;           // + h * 2 * kPSubBytes
+    const uint32_t swz = (uint32_t)(row & 7);
+    const float sl2 = p.scale_log2;
+    uint32_t cnt[2] = {0, 0}, u = 0, n = 0, corr = 0;
+    float m_run = 0.f, l_run = 0.f;
+
+    // maximum of the nv valid columns (of this thread's 64) of S half h
+    auto row_max = [&](int h, int nv, float m) -> float {
+      if (nv <= 0) return m;
+      uint32_t v0[32], v1[32];
+      tmem_ld_x32(s_col + h * kHalfKV, v0);
+      if (nv > 32) tmem_ld_x32(s_col + h * kHalfKV + 32, v1);
+      tmem_wait_ld();
+      float a0 = m, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+      if (nv >= 32) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          a0 = fmaxf(a0, fmaxf(__uint_as_float(v0[j]), __uint_as_float(v0[j + 1])));
+          a1 = fmaxf(a1, fmaxf(__uint_as_float(v0[j + 2]), __uint_as_float(v0[j + 3])));
+          a2 = fmaxf(a2, fmaxf(__uint_as_float(v0[j + 4]), __uint_as_float(v0[j + 5])));
+          a3 = fmaxf(a3, fmaxf(__uint_as_float(v0[j + 6]), __uint_as_float(v0[j + 7])));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nv) a0 = fmaxf(a0, __uint_as_float(v0[j]));
+      }
+      if (nv == 64) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          a0 = fmaxf(a0, fmaxf(__uint_as_float(v1[j]), __uint_as_float(v1[j + 1])));
+          a1 = fmaxf(a1, fmaxf(__uint_as_float(v1[j + 2]), __uint_as_float(v1[j + 3])));
+          a2 = fmaxf(a2, fmaxf(__uint_as_float(v1[j + 4]), __uint_as_float(v1[j + 5])));
+          a3 = fmaxf(a3, fmaxf(__uint_as_float(v1[j + 6]), __uint_as_float(v1[j + 7])));
+        }
+      } else if (nv > 32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (32 + j < nv) a1 = fmaxf(a1, __uint_as_float(v1[j]));
+      }
+      return fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+    };
+
+    // p = exp2(s * scale - M) for 32 columns (chunk c of this thread's 64), written as 16-bit into the swizzled
+    // A tile of the PV product; returns the row-sum contribution
+    auto exp_chunk = [&](int h, int c, int nv, float M) -> float {
+      uint32_t v[32], pk[16];
+      tmem_ld_x32(s_col + h * kHalfKV + c * 32, v);
+      tmem_wait_ld();
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      if (c * 32 + 32 <= nv) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float e0 = fast_exp2(fmaf(__uint_as_float(v[j]), sl2, -M));
+          const float e1 = fast_exp2(fmaf(__uint_as_float(v[j + 1]), sl2, -M));
+          const float e2 = fast_exp2(fmaf(__uint_as_float(v[j + 2]), sl2, -M));
+          const float e3 = fast_exp2(fmaf(__uint_as_float(v[j + 3]), sl2, -M));
+          s0 += e0;
+          s1 += e1;
+          s2 += e2;
+          s3 += e3;
+          pk[j >> 1] = pack2<kBf16>(e0, e1);
+          pk[(j >> 1) + 1] = pack2<kBf16>(e2, e3);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float e0 = fast_exp2(fmaf(__uint_as_float(v[j]), sl2, -M));
+          float e1 = fast_exp2(fmaf(__uint_as_float(v[j + 1]), sl2, -M));
+          if (c * 32 + j >= nv) e0 = 0.f;
+          if (c * 32 + j + 1 >= nv) e1 = 0.f;
+          s0 += e0;
+          s1 += e1;
+          pk[j >> 1] = pack2<kBf16>(e0, e1);
+        }
+      }
+      const uint32_t base = p_row + h * (2 * kPSubBytes);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t chunk = (uint32_t)(c * 4 + q) ^ swz;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + chunk * 16), "r"(pk[4 * q]),
+                     "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                     : "memory");
+      }
+      return (s0 + s1) + (s2 + s3);
+    };
+    auto exp_half = [&](int h, int nv, float M) -> float {
+      if (nv <= 0) return 0.f;   // this thread's stage of the half does not exist: the tensor core skips it
+      float s = exp_chunk(h, 0, nv, M);
+      if (nv > 32) {
+        s += exp_chunk(h, 1, nv, M);
+      } else {
+        // columns 32..63 of a stage the tensor core will read: P must be exactly zero there
+        const uint32_t base = p_row + h * (2 * kPSubBytes);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t chunk = (uint32_t)(4 + q) ^ swz;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + chunk * 16), "r"(0u) : "memory");
+        }
+      }
+      return s;
+    };
+
+    for_each_group(p, [&](const GroupInfo& G) {
+      const int nvA = max(0, min(G.rowsA - wg * kStageKV, kStageKV));
+      const int nvB = max(0, min(G.rowsB - wg * kStageKV, kStageKV));
+      // ---- pass 1: row maximum over the whole group
+      mbar_wait(&s_full[0], cnt[0] & 1);
+      tc_fence_after_sync();
+      float m = row_max(0, nvA, -INFINITY);
+      if (G.rowsB) {
+        mbar_wait(&s_full[1], cnt[1] & 1);
         tc_fence_after_sync();
-        // pass 1: row maximum over this half
-        float m = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          if (c * 32 < nvalid) {
-            uint32_t v[32];
-            tmem_ld_x32(tmem_base + lane_addr + kTmemS + col0 + c * 32, v);
-            tmem_wait_ld();
-            if (c * 32 + 32 <= nvalid) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (c * 32 + j < nvalid) m = fmaxf(m, __uint_as_float(v[j]));
-            }
-          }
+        m = row_max(1, nvB, m);
+      }
+      m *= sl2;
+      float* mx = sMax + (u & 1) * 256;
+      mx[wg * 128 + row] = m;
+      named_bar_sync(1, 256);
+      float M = fmaxf(m, mx[(wg ^ 1) * 128 + row]);
+      if (G.first_of_item) {
+        l_run = 0.f;
+      } else {
+        // online softmax across groups: publish the factor the epilogue warps rescale O with
+        M = fmaxf(m_run, M);
+        const float alpha = fast_exp2(m_run - M);
+        l_run *= alpha;
+        if (wg == 0) {
+          tmem_st_x1(tmem_base + lane_addr + kTmemAlpha + (corr & 1), __float_as_uint(alpha));
+          tmem_wait_st();
+          tc_fence_before_sync();
+          mbar_arrive(alpha_full);
         }
-        m *= p.scale_log2;
-        float* mx = sMax + par * 256;
-        mx[wg * 128 + row] = m;
-        named_bar_sync(1, 256);
-        const float M = fmaxf(m, mx[(wg ^ 1) * 128 + row]);
-        // P(n) may be written once PV(n-1) has consumed P(n-1)
-        mbar_wait(pv_done, par ^ 1);
-        // pass 2: p = exp2(s * scale - M), row sum, 16-bit P into the swizzled A tile
-        float sum = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          if (c * 32 < nvalid) {
-            uint32_t v[32];
-            tmem_ld_x32(tmem_base + lane_addr + kTmemS + col0 + c * 32, v);
-            tmem_wait_ld();
-            uint32_t pk[16];
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              float e0 = fast_exp2(fmaf(__uint_as_float(v[j]), p.scale_log2, -M));
-              float e1 = fast_exp2(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -M));
-              if (c * 32 + j >= nvalid) e0 = 0.f;
-              if (c * 32 + j + 1 >= nvalid) e1 = 0.f;
-              sum += e0 + e1;
-              pk[j >> 1] = pack2<kBf16>(e0, e1);
-            }
-            const int sub = (col0 + c * 32) >> 6;
-            const uint32_t base = p_row + sub * (kBlockQ * 128);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint32_t chunk = (uint32_t)((c & 1) * 4 + q) ^ (uint32_t)(row & 7);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + chunk * 16), "r"(pk[4 * q]),
-                           "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
-                           : "memory");
-            }
-          } else if (c * 32 < n_kb * kBlockKV - col0) {
-            // columns beyond Skv but inside a kv block the MMA will read: P must be exactly zero
-            const int sub = (col0 + c * 32) >> 6;
-            const uint32_t base = p_row + sub * (kBlockQ * 128);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint32_t chunk = (uint32_t)((c & 1) * 4 + q) ^ (uint32_t)(row & 7);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + chunk * 16), "r"(0u) : "memory");
-            }
-          }
-        }
-        // S(n) has been consumed: the MMA warp may overwrite it with S(n+1)
-        tc_fence_before_sync();
-        mbar_arrive(s_empty);
-        // publish the row sum (TMEM, read by the epilogue) and P (smem, read by the tensor core)
-        {
-          uint32_t sv = __float_as_uint(sum);
-          asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tmem_base + lane_addr + kTmemSum +
-                                                                                   2 * par + wg),
-                       "r"(sv)
-                       : "memory");
+        ++corr;
+      }
+      m_run = M;
+      // ---- pass 2, half A
+      mbar_wait(&pv_done[0], (cnt[0] & 1) ^ 1);   // P_A of the previous group has been consumed
+      l_run += exp_half(0, nvA, M);
+      if (G.last_of_item && G.rowsB == 0) {
+        tmem_st_x1(tmem_base + lane_addr + kTmemSum + 2 * (n & 1) + wg, __float_as_uint(l_run));
+        tmem_wait_st();
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(&s_empty[0]);
+      mbar_arrive(&p_full[0]);
+      ++cnt[0];
+      // ---- pass 2, half B
+      if (G.rowsB) {
+        mbar_wait(&pv_done[1], (cnt[1] & 1) ^ 1);
+        l_run += exp_half(1, nvB, M);
+        if (G.last_of_item) {
+          tmem_st_x1(tmem_base + lane_addr + kTmemSum + 2 * (n & 1) + wg, __float_as_uint(l_run));
           tmem_wait_st();
         }
         fence_proxy_async_smem();
         tc_fence_before_sync();
-        mbar_arrive(p_full);
+        mbar_arrive(&s_empty[1]);
+        mbar_arrive(&p_full[1]);
+        ++cnt[1];
       }
-    }
+      if (G.last_of_item) ++n;
+      ++u;
+    });
   } else if (warp >= 12) {
-    // ------------------------------------------------------------------ epilogue
+    // ------------------------------------------------------------------ epilogue / correction
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    const uint32_t os_row = smem_u32(sOs) + row * 16;   // chunk c lives at os_row + c * 2048
-    uint32_t n = 0;
+    const uint32_t o_col = tmem_base + lane_addr + kTmemO;
+    const uint32_t os_col = tmem_base + lane_addr + kTmemOs;
+    const int tiles = p.B * p.H * p.n_qt;
+    uint32_t n = 0, corr = 0, cntB = 0;
     float ns_tile = 0.f;  // |O_self|^2 of the current stream (meaningful on the reducing thread)
-    for (int64_t st = blockIdx.x; st < n_streams; st += gridDim.x) {
-      DS_DECODE_STREAM(st);
-      const bool row_ok = qt * kBlockQ + row < p.Sq;
-      for (int it = 0; it < n_items; ++it, ++n) {
-        const uint32_t par = n & 1;
-        const bool self = p.self_first && it == 0;
-        mbar_wait(pv_done, par);
+    for_each_group(p, [&](const GroupInfo& G) {
+      if (!G.first_of_item) {
+        // rescale O by the factors of this group once the previous group's PV has landed (the previous group of an
+        // item is always complete, so its last product is PV_B)
+        mbar_wait(alpha_full, corr & 1);
+        mbar_wait(&pv_done[1], (cntB - 1) & 1);
         tc_fence_after_sync();
-        float inv_l;
-        {
-          uint32_t s0, s1;
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];"
-                       : "=r"(s0), "=r"(s1)
-                       : "r"(tmem_base + lane_addr + kTmemSum + 2 * par)
-                       : "memory");
-          tmem_wait_ld();
-          inv_l = 1.0f / (__uint_as_float(s0) + __uint_as_float(s1));
-        }
-        float dot = 0.f, nc = 0.f, sq = 0.f;
-        uint8_t* out_row = nullptr;
-        if (p.mode == ATTN_MODE_STORE)
-          out_row = static_cast<uint8_t*>(p.out) +
-                    2 * ((int64_t)b * p.out_sb + (int64_t)h * p.out_sh + (int64_t)(qt * kBlockQ + row) * p.out_ss);
+        const float alpha = __uint_as_float(tmem_ld_x1(tmem_base + lane_addr + kTmemAlpha + (corr & 1)));
+        tmem_wait_ld();
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll 1
-        for (int c = 0; c < C::D_PAD / 16; ++c) {
-          uint32_t v[16];
-          tmem_ld_x16(tmem_base + lane_addr + kTmemO + c * 16, v);
-          tmem_wait_ld();
-          if (c == C::D_PAD / 16 - 1) {
-            // O(n) is in registers: the MMA warp may start PV(n+1)
-            tc_fence_before_sync();
-            mbar_arrive(o_empty);
+          for (int c = 0; c < C::D_PAD / 16; ++c) {
+            uint32_t v[16];
+            tmem_ld_x16(o_col + c * 16, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
+            tmem_st_x16(o_col + c * 16, v);
           }
+          tmem_wait_st();
+        }
+        tc_fence_before_sync();
+        mbar_arrive(corr_done);
+        ++corr;
+      }
+      if (G.rowsB) ++cntB;
+      if (!G.last_of_item) return;
+
+      const uint32_t par = n & 1;
+      const bool row_ok = G.qt * kBlockQ + row < p.Sq;
+      mbar_wait(o_full, par);
+      tc_fence_after_sync();
+      float inv_l;
+      {
+        uint32_t s0, s1;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];"
+                     : "=r"(s0), "=r"(s1)
+                     : "r"(tmem_base + lane_addr + kTmemSum + 2 * par)
+                     : "memory");
+        tmem_wait_ld();
+        inv_l = 1.0f / (__uint_as_float(s0) + __uint_as_float(s1));
+      }
+      float acc0 = 0.f, acc1 = 0.f;   // cosine: dot / |Oc|^2 (cross), |Os|^2 (self); mse: sum of squared differences
+      uint8_t* out_row = nullptr;
+      if constexpr (MODE == ATTN_MODE_STORE)
+        out_row = static_cast<uint8_t*>(p.out) + 2 * ((int64_t)G.b * p.out_sb + (int64_t)G.h * p.out_sh +
+                                                     (int64_t)(G.qt * kBlockQ + row) * p.out_ss);
+#pragma unroll 1
+      for (int c = 0; c < C::D_PAD / 16; ++c) {
+        uint32_t v[16];
+        tmem_ld_x16(o_col + c * 16, v);
+        tmem_wait_ld();
+        if (c == C::D_PAD / 16 - 1) {
+          // O is in registers: the MMA warp may start the next item's PV
+          tc_fence_before_sync();
+          mbar_arrive(o_empty);
+        }
+        if constexpr (MODE == ATTN_MODE_STORE) {
           uint32_t pk[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             pk[j] = pack2<kBf16>(__uint_as_float(v[2 * j]) * inv_l, __uint_as_float(v[2 * j + 1]) * inv_l);
-          if (p.mode == ATTN_MODE_STORE) {
-            if (row_ok) {
+          if (row_ok) {
 #pragma unroll
-              for (int hlf = 0; hlf < 2; ++hlf) {
-                if (c * 16 + hlf * 8 < D) {
-                  uint4 u = make_uint4(pk[4 * hlf], pk[4 * hlf + 1], pk[4 * hlf + 2], pk[4 * hlf + 3]);
-                  *reinterpret_cast<uint4*>(out_row + (c * 16 + hlf * 8) * 2) = u;
-                }
+            for (int hlf = 0; hlf < 2; ++hlf) {
+              if (c * 16 + hlf * 8 < D) {
+                uint4 w = make_uint4(pk[4 * hlf], pk[4 * hlf + 1], pk[4 * hlf + 2], pk[4 * hlf + 3]);
+                *reinterpret_cast<uint4*>(out_row + (c * 16 + hlf * 8) * 2) = w;
               }
             }
-          } else if (self) {
+          }
+        } else if (G.self) {
+          // O_self is rounded to the input dtype (as the reference's SDPA output is) and kept in TMEM
+          uint32_t pk[8];
 #pragma unroll
-            for (int hlf = 0; hlf < 2; ++hlf)
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(os_row + (2 * c + hlf) * 2048),
-                           "r"(pk[4 * hlf]), "r"(pk[4 * hlf + 1]), "r"(pk[4 * hlf + 2]), "r"(pk[4 * hlf + 3])
-                           : "memory");
-            if (row_ok) {
+          for (int j = 0; j < 8; ++j)
+            pk[j] = pack2<kBf16>(__uint_as_float(v[2 * j]) * inv_l, __uint_as_float(v[2 * j + 1]) * inv_l);
+          tmem_st_x8(os_col + c * 8, pk);
+          if constexpr (MODE == ATTN_MODE_COS) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float2 o = unpack2<kBf16>(pk[j]);
-                nc = fmaf(o.x, o.x, nc);
-                nc = fmaf(o.y, o.y, nc);
-              }
+            for (int j = 0; j < 8; ++j) {
+              const float2 o = unpack2<kBf16>(pk[j]);
+              acc0 = fmaf(o.x, o.x, acc0);
+              acc1 = fmaf(o.y, o.y, acc1);
+            }
+          }
+        } else {
+          uint32_t os[8];
+          tmem_ld_x8(os_col + c * 8, os);
+          tmem_wait_ld();
+          if constexpr (MODE == ATTN_MODE_COS) {
+            // unnormalised: dot = inv_l * sum o s, |Oc|^2 = inv_l^2 * sum o^2 (applied once per row below)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 s = unpack2<kBf16>(os[j]);
+              const float ox = __uint_as_float(v[2 * j]), oy = __uint_as_float(v[2 * j + 1]);
+              acc0 = fmaf(ox, s.x, acc0);
+              acc0 = fmaf(oy, s.y, acc0);
+              acc1 = fmaf(ox, ox, acc1);
+              acc1 = fmaf(oy, oy, acc1);
             }
           } else {
-            uint32_t os[8];
 #pragma unroll
-            for (int hlf = 0; hlf < 2; ++hlf)
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                           : "=r"(os[4 * hlf]), "=r"(os[4 * hlf + 1]), "=r"(os[4 * hlf + 2]), "=r"(os[4 * hlf + 3])
-                           : "r"(os_row + (2 * c + hlf) * 2048)
-                           : "memory");
-            if (row_ok) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float2 o = unpack2<kBf16>(pk[j]);
-                float2 s = unpack2<kBf16>(os[j]);
-                dot = fmaf(o.x, s.x, dot);
-                dot = fmaf(o.y, s.y, dot);
-                nc = fmaf(o.x, o.x, nc);
-                nc = fmaf(o.y, o.y, nc);
-                float dx = o.x - s.x, dy = o.y - s.y;
-                sq = fmaf(dx, dx, sq);
-                sq = fmaf(dy, dy, sq);
-              }
-            }
-          }
-        }
-        if (p.mode == ATTN_MODE_AAS) {
-          // fixed-order reduction over the 128 rows: shuffle tree, then warps 0..3 in order
-          dot = warp_sum(dot);
-          nc = warp_sum(nc);
-          sq = warp_sum(sq);
-          float* red = sRed + par * 16;
-          if (lane == 0) {
-            red[quad * 4 + 0] = dot;
-            red[quad * 4 + 1] = nc;
-            red[quad * 4 + 2] = sq;
-          }
-          named_bar_sync(2, 128);
-          if (quad == 0 && lane == 0) {
-            float d = red[0] + red[4] + red[8] + red[12];
-            float c2 = red[1] + red[5] + red[9] + red[13];
-            float s2 = red[2] + red[6] + red[10] + red[14];
-            if (self) {
-              ns_tile = c2;
-            } else {
-              const int t = t0 + it - p.self_first;
-              p.part[(size_t)t * (BH * p.n_qt) + bh * p.n_qt + qt] = make_float4(d, c2, ns_tile, s2);
+            for (int j = 0; j < 8; ++j) {
+              const float2 s = unpack2<kBf16>(os[j]);
+              const float dx = fmaf(__uint_as_float(v[2 * j]), inv_l, -s.x);
+              const float dy = fmaf(__uint_as_float(v[2 * j + 1]), inv_l, -s.y);
+              acc0 = fmaf(dx, dx, acc0);
+              acc1 = fmaf(dy, dy, acc1);
             }
           }
         }
       }
-    }
+      if constexpr (MODE != ATTN_MODE_STORE) {
+        if (G.self) tmem_wait_st();
+        float r0, r1;   // cross: (dot, |Oc|^2) or (sq, 0); self: (|Os|^2, 0)
+        if (G.self) {
+          r0 = acc0 + acc1;
+          r1 = 0.f;
+        } else if constexpr (MODE == ATTN_MODE_COS) {
+          r0 = acc0 * inv_l;
+          r1 = acc1 * inv_l * inv_l;
+        } else {
+          r0 = acc0 + acc1;
+          r1 = 0.f;
+        }
+        if (!row_ok) r0 = r1 = 0.f;
+        // fixed-order reduction over the 128 rows: shuffle tree, then warps 0..3 in order
+        r0 = warp_sum(r0);
+        r1 = warp_sum(r1);
+        float* red = sRed + par * 16;
+        if (lane == 0) {
+          red[quad * 4 + 0] = r0;
+          red[quad * 4 + 1] = r1;
+        }
+        named_bar_sync(2, 128);
+        if (quad == 0 && lane == 0) {
+          const float t0 = (red[0] + red[4]) + (red[8] + red[12]);
+          const float t1 = (red[1] + red[5]) + (red[9] + red[13]);
+          if (G.self) {
+            ns_tile = t0;
+          } else if constexpr (MODE == ATTN_MODE_COS) {
+            p.part[(size_t)G.entry * tiles + G.bh * p.n_qt + G.qt] = make_float4(t0, t1, ns_tile, 0.f);
+          } else {
+            p.part[(size_t)G.entry * tiles + G.bh * p.n_qt + G.qt] = make_float4(0.f, 0.f, 0.f, t0);
+          }
+        }
+      }
+      ++n;
+    });
   }
-#undef DS_DECODE_STREAM
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
@@ -656,7 +847,28 @@ static int make_map(CUtensorMap* m, const ds_tensor5& t, int subw, int rows) {
 struct AttnLaunch {
   ds_tensor5 q, ks, vs, k, v;
   AttnParams p;
+  int mode;   // ATTN_MODE_*
 };
+
+template <int D, bool kBf16, int MODE>
+static int launch_attn_one(const AttnLaunch& a, int grid, const CUtensorMap& mq, const CUtensorMap& mks,
+                           const CUtensorMap& mvs, const CUtensorMap& mk, const CUtensorMap& mv, cudaStream_t st) {
+  using C = AttnCfg<D>;
+  DS_CUDA_TRY(cudaFuncSetAttribute(aas_attn_kernel<D, kBf16, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   C::SMEM_BYTES));
+  aas_attn_kernel<D, kBf16, MODE><<<grid, kAttnThreads, C::SMEM_BYTES, st>>>(mq, mks, mvs, mk, mv, a.p);
+  return DS_OK;
+}
+
+template <int D, bool kBf16>
+static int launch_attn_mode(const AttnLaunch& a, int grid, const CUtensorMap& mq, const CUtensorMap& mks,
+                            const CUtensorMap& mvs, const CUtensorMap& mk, const CUtensorMap& mv, cudaStream_t st) {
+  switch (a.mode) {
+    case ATTN_MODE_COS: return launch_attn_one<D, kBf16, ATTN_MODE_COS>(a, grid, mq, mks, mvs, mk, mv, st);
+    case ATTN_MODE_MSE: return launch_attn_one<D, kBf16, ATTN_MODE_MSE>(a, grid, mq, mks, mvs, mk, mv, st);
+    default: return launch_attn_one<D, kBf16, ATTN_MODE_STORE>(a, grid, mq, mks, mvs, mk, mv, st);
+  }
+}
 
 template <int D>
 static int launch_attn_d(const AttnLaunch& a, cudaStream_t st) {
@@ -664,22 +876,19 @@ static int launch_attn_d(const AttnLaunch& a, cudaStream_t st) {
   CUtensorMap mq, mks, mvs, mk, mv;
   int rc;
   if ((rc = make_map(&mq, a.q, C::SUBW, kBlockQ)) != DS_OK) return rc;
-  if ((rc = make_map(&mks, a.ks, C::SUBW, kBlockKV)) != DS_OK) return rc;
-  if ((rc = make_map(&mvs, a.vs, C::SUBW, kBlockKV)) != DS_OK) return rc;
-  if ((rc = make_map(&mk, a.k, C::SUBW, kBlockKV)) != DS_OK) return rc;
-  if ((rc = make_map(&mv, a.v, C::SUBW, kBlockKV)) != DS_OK) return rc;
+  if ((rc = make_map(&mks, a.ks, C::SUBW, kStageKV)) != DS_OK) return rc;
+  if ((rc = make_map(&mvs, a.vs, C::SUBW, kStageKV)) != DS_OK) return rc;
+  if ((rc = make_map(&mk, a.k, C::SUBW, kStageKV)) != DS_OK) return rc;
+  if ((rc = make_map(&mv, a.v, C::SUBW, kStageKV)) != DS_OK) return rc;
   const int64_t n_streams = (int64_t)a.p.n_groups * a.p.B * a.p.H * a.p.n_qt;
   int grid = sm_count();
   if (n_streams < grid) grid = (int)n_streams;
   if (grid <= 0) return DS_OK;
   profile_begin(st);
-  if (a.q.dtype == DS_BF16) {
-    DS_CUDA_TRY(cudaFuncSetAttribute(aas_attn_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    aas_attn_kernel<D, true><<<grid, kAttnThreads, C::SMEM_BYTES, st>>>(mq, mks, mvs, mk, mv, a.p);
-  } else {
-    DS_CUDA_TRY(cudaFuncSetAttribute(aas_attn_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    aas_attn_kernel<D, false><<<grid, kAttnThreads, C::SMEM_BYTES, st>>>(mq, mks, mvs, mk, mv, a.p);
-  }
+  int rc2 = DS_OK;
+  if (a.q.dtype == DS_BF16) rc2 = launch_attn_mode<D, true>(a, grid, mq, mks, mvs, mk, mv, st);
+  else rc2 = launch_attn_mode<D, false>(a, grid, mq, mks, mvs, mk, mv, st);
+  if (rc2 != DS_OK) return rc2;
   profile_end(st);
   DS_CUDA_TRY(cudaGetLastError());
   return DS_OK;
@@ -719,16 +928,13 @@ static int prepare(AttnLaunch& a, float scale, const char* who) {
     return fail(DS_ERR_INVALID, "%s: k_self / v_self must hold the same images as q", who);
   if (a.k.size[0] != a.v.size[0]) return fail(DS_ERR_INVALID, "%s: k and v must hold the same images", who);
   const int64_t Skv = a.k.size[3];
-  if (Skv > kMaxKV)
-    return fail(DS_ERR_UNSUPPORTED, "%s: kv length %lld > %d is not built yet (single-pass softmax kernel)", who,
-                (long long)Skv, kMaxKV);
+  if (Skv > INT32_MAX / 2) return fail(DS_ERR_INVALID, "%s: kv length too large", who);
   const int64_t D = a.q.size[4];
   a.p.B = (int)a.q.size[1];
   a.p.H = (int)a.q.size[2];
   a.p.Sq = (int)a.q.size[3];
   a.p.Skv = (int)Skv;
   a.p.n_qt = (int)((a.q.size[3] + kBlockQ - 1) / kBlockQ);
-  a.p.n_kb = (int)((Skv + kBlockKV - 1) / kBlockKV);
   const float sc = scale > 0.f ? scale : 1.0f / sqrtf((float)D);
   a.p.scale_log2 = sc * 1.4426950408889634f;
   return ds_device_ok();
@@ -786,7 +992,7 @@ int ds_attn_fwd(ds_tensor4 q, ds_tensor4 k, ds_tensor4 v, float scale, ds_tensor
   a.p.kv_idx = meta + 3;
   a.p.n_groups = 1;
   a.p.self_first = 0;
-  a.p.mode = ATTN_MODE_STORE;
+  a.mode = ATTN_MODE_STORE;
   a.p.part = nullptr;
   a.p.out = out.ptr;
   a.p.out_sb = out.stride[0];
@@ -831,7 +1037,7 @@ int ds_aas_groups(ds_tensor5 q, ds_tensor5 k_self, ds_tensor5 v_self, ds_tensor5
   a.p.kv_idx = kv_idx;
   a.p.n_groups = (int)n_groups;
   a.p.self_first = 1;
-  a.p.mode = ATTN_MODE_AAS;
+  a.mode = (mode == DS_SIM_MSE) ? ATTN_MODE_MSE : ATTN_MODE_COS;
   a.p.part = part;
   a.p.out = nullptr;
   a.p.out_sb = a.p.out_sh = a.p.out_ss = 0;
@@ -991,7 +1197,7 @@ int ds_aas_matrix(ds_tensor5 q, ds_tensor5 k_self, ds_tensor5 v_self, ds_tensor5
   a.p.kv_idx = kv;
   a.p.n_groups = (int)G;
   a.p.self_first = 1;
-  a.p.mode = ATTN_MODE_AAS;
+  a.mode = (mode == DS_SIM_MSE) ? ATTN_MODE_MSE : ATTN_MODE_COS;
   a.p.part = part;
   a.p.out = nullptr;
   a.p.out_sb = a.p.out_sh = a.p.out_ss = 0;

@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 CASES = ["reduce", "simmat", "attn_pv", "attn_qk", "attn_d160", "attn_d64", "attn_d72", "attn_d40", "attn_d80",
-         "attn_d128", "attn_tails", "aas_pairs", "aas_groups", "aas_matrix", "perf"]
+         "attn_d128", "attn_tails", "attn_long", "aas_pairs", "aas_groups", "aas_matrix", "perf"]
 
 
 def report(name, got, ref, tol, row_block=32, col_block=32):
@@ -222,6 +222,21 @@ def case_attn_tails():
     return ok
 
 
+def case_attn_long():
+    import torch
+
+    # kv lengths beyond one 256-row group: online softmax across groups (SDXL / SD-1.5 high-resolution layers)
+    ok = _attn_case(1, 2, 128, 320, 64, torch.float16)       # 1 full group + a 64-row tail (half A only)
+    ok &= _attn_case(1, 2, 200, 448, 64, torch.float16)      # tail group with a partial half B
+    ok &= _attn_case(1, 2, 256, 512, 64, torch.bfloat16)
+    ok &= _attn_case(2, 4, 1024, 1024, 64, torch.float16)    # SDXL up_blocks[0]-like
+    ok &= _attn_case(1, 2, 1024, 1024, 80, torch.float16)    # SD-1.5 up_blocks[1]-like
+    ok &= _attn_case(1, 2, 512, 4096, 40, torch.float16)     # SD-1.5 up_blocks[2]-like
+    ok &= _attn_case(1, 2, 4096, 4096, 64, torch.bfloat16)   # SDXL up_blocks[1]-like
+    ok &= _attn_case(1, 1, 300, 700, 160, torch.float16)
+    return ok
+
+
 def _pairs_setup(shape, n_pairs, dtype, seed=0, layout="sd"):
     from diffsim_b200 import synth
 
@@ -238,7 +253,8 @@ def case_aas_pairs():
 
     ok = True
     for shape, dtype, npairs in (((2, 8, 256, 160), torch.float16, 4), ((2, 8, 256, 160), torch.bfloat16, 3),
-                                 ((2, 16, 256, 72), torch.float16, 3), ((2, 4, 64, 64), torch.float16, 3)):
+                                 ((2, 16, 256, 72), torch.float16, 3), ((2, 4, 64, 64), torch.float16, 3),
+                                 ((2, 4, 640, 64), torch.float16, 2), ((1, 2, 1024, 64), torch.bfloat16, 2)):
         images, pairs = _pairs_setup(shape, npairs, dtype)
         q, k, v = synth.stack_cache(images, "cuda")
         for mode in ("cosine", "mse"):
