@@ -2,11 +2,11 @@
 //
 // One persistent, warp-specialised CTA per SM:
 //
-//   warp 0        TMA producer   Q tile (per stream) and a ring of 64-row K / V stages
-//   warp 1        MMA issuer     tcgen05.mma: S = Q K^T (fp32, TMEM), O (+)= P V (fp32, TMEM)
+//   warp 0        TMA producer   Q tile (per stream) and a ring of 128-row K / V stages
+//   warp 1        MMA issuer     tcgen05.mma: S = Q K^T (fp32, TMEM), O (+)= P V (fp32, TMEM; P read from TMEM)
 //   warp 2        TMEM allocator
 //   warps 4-11    softmax        256 threads; thread = (q row, 64 of the 128 kv columns of an S half);
-//                                S (TMEM) -> exp2 -> P (16-bit, 128B-swizzled smem, the A operand of PV)
+//                                S (TMEM) -> exp2 -> P (16-bit, written IN PLACE over S: the A operand of PV)
 //   warps 12-15   epilogue       O (TMEM) -> 1/l ->
 //                                  self item : O_self rounded to the input dtype, kept on chip (TMEM), |O_self|^2
 //                                  cross item: dot(O_cross,O_self), |O_cross|^2 or sum (O_cross-O_self)^2
@@ -16,17 +16,24 @@
 // Work decomposition.  A "stream" is (group, b, h, 128-row q tile): the Q tile stays resident while the kv
 // images of the group ("items") stream through; the first item of a group is the query image's own K/V (the
 // self attention of diffsim/diffsim.py:179-180), whose output never leaves the SM.  An item is cut into kv
-// GROUPS of 256 rows, a group into two HALVES (A, B) of 128 rows with their own S columns in TMEM and their
-// own P buffer in shared memory, a half into 64-row ring stages.
+// GROUPS of 256 rows, a group into two HALVES (A, B) of 128 rows = one ring stage = one N=128 MMA slice with
+// its own 128 TMEM columns.
+//
+// Why this shape: the kernel is bound by shared-memory bandwidth (128 B/clk/SM), not by the tensor pipe, as
+// soon as operands are re-read from shared memory: an SS-mode MMA with N=64 reads 6 KB per 32 tensor-clocks.
+// So S is produced by N=128 MMAs (Q is re-read only twice per item), P never touches shared memory (the
+// softmax warps overwrite S in TMEM with 16-bit P and the PV MMA takes its A operand from TMEM), and O_self
+// lives in TMEM as well.  Shared memory then carries only TMA writes + one read of K and V + two reads of Q.
 //
 // Softmax.  The row maximum is taken over the whole group before any exponential (exact two-pass softmax:
 // for kv <= 256 -- SD-1.5 up_blocks[0], DiT -- there is exactly one group and no rescaling anywhere); across
 // groups the running maximum / sum are carried in registers and O is rescaled in TMEM by the epilogue warps
 // (skipped per warp when no row maximum moved).
 //
-// Pipeline.  The MMA warp issues, in this fixed order, QK_A(u+1), PV_A(u), QK_B(u+1), PV_B(u): as soon as the
-// softmax warps have turned half A of group u into P_A they start on half B while the tensor core already
-// recomputes S_A for the next group and consumes P_A.  The TMA producer feeds the ring in the same order.
+// Pipeline.  The MMA warp issues, in this fixed order, PV_A(u), QK_A(u+1), PV_B(u), QK_B(u+1): tcgen05 ops of
+// one thread execute in issue order, so QK_A(u+1) may overwrite the columns PV_A(u) reads P from without any
+// barrier; while the tensor core works on half A the softmax warps turn half B into P.  The TMA producer feeds
+// the ring in the same order.
 //
 // Replaces diffsim/diffsim.py:177-197 (diffsim_xl.py:135-155, diffsim_dit.py:130-142).
 // Algorithmic work per directional attention: 4*B*H*Sq*Skv*D flops.
@@ -39,17 +46,15 @@ enum : int { ATTN_MODE_COS = 0, ATTN_MODE_MSE = 1, ATTN_MODE_STORE = 2 };
 
 constexpr int kAttnThreads = 512;
 constexpr int kBlockQ = 128;     // q rows per tile == TMEM lanes
-constexpr int kStageKV = 64;     // kv rows per ring stage
-constexpr int kHalfKV = 128;     // kv rows per S half
+constexpr int kHalfKV = 128;     // kv rows per S half == per ring stage
 constexpr int kGroupKV = 256;    // kv rows per softmax group (two halves)
 constexpr int kTmemCols = 512;
-constexpr int kTmemS = 0;        // S_A: columns [0,128), S_B: [128,256)
+constexpr int kTmemS = 0;        // S_A: columns [0,128), S_B: [128,256); P of the thread's 64 kv columns
+                                 // overwrites the first 32 of its own 64 S columns
 constexpr int kTmemO = 256;      // O: [256, 256 + D_PAD)
 constexpr int kTmemOs = 416;     // O_self, packed 16-bit: [416, 416 + D_PAD/2)
 constexpr int kTmemSum = 496;    // row sums: 496 + 2 * (item parity) + (column half of the thread)
 constexpr int kTmemAlpha = 500;  // online-softmax rescale factors: 500 + (correction parity)
-constexpr int kPSubBytes = kBlockQ * 128;       // one [128 x 64] 128B-swizzled P sub-tile: 16 KB
-constexpr int kPBytes = 4 * kPSubBytes;         // P_A (sub-tiles 0,1) and P_B (2,3): 64 KB
 
 template <int D>
 struct AttnCfg {
@@ -61,13 +66,13 @@ struct AttnCfg {
   static constexpr int CPS = SUBW / 16;                           // 16-element K chunks per sub-tile
   static constexpr int Q_SUB_BYTES = kBlockQ * SUB_BYTES;
   static constexpr int Q_BYTES = NSUB * Q_SUB_BYTES;
-  static constexpr int KV_SUB_BYTES = kStageKV * SUB_BYTES;
+  static constexpr int KV_SUB_BYTES = kHalfKV * SUB_BYTES;
   static constexpr int STAGE_BYTES = NSUB * KV_SUB_BYTES;
   static constexpr int MISC_BYTES = 2048 /*max exchange*/ + 128 /*epilogue reduce*/ + 512 /*barriers*/;
   static constexpr int kMaxSmem = 232448;
-  static constexpr int STAGES_RAW = (kMaxSmem - Q_BYTES - kPBytes - MISC_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES_RAW = (kMaxSmem - Q_BYTES - MISC_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 12 ? 12 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = Q_BYTES + kPBytes + STAGES * STAGE_BYTES + MISC_BYTES;
+  static constexpr int SMEM_BYTES = Q_BYTES + STAGES * STAGE_BYTES + MISC_BYTES;
   static_assert(STAGES >= 4, "not enough shared memory for the K/V ring");
   static_assert(kTmemO + D_PAD <= kTmemOs && kTmemOs + D_PAD / 2 <= kTmemSum, "TMEM budget");
   static_assert(Q_BYTES % 1024 == 0 && STAGE_BYTES % 1024 == 0, "swizzle atoms need 1024-byte aligned tiles");
@@ -142,18 +147,15 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   using C = AttnCfg<D>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
-  uint8_t* sP = sQ + C::Q_BYTES;
-  uint8_t* sRing = sP + kPBytes;
+  uint8_t* sRing = sQ + C::Q_BYTES;
   float* sMax = reinterpret_cast<float*>(sRing + C::STAGES * C::STAGE_BYTES);  // [2 parity][2 col half][128]
   float* sRed = sMax + 512;                                                    // [2 parity][4 warps][4]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 32);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
   uint64_t* s_full = bars + 2;      // [2] S half written by the tensor core
-  uint64_t* s_empty = bars + 4;     // [2] S half consumed by the softmax warps
-  uint64_t* p_full = bars + 6;      // [2] P half written by the softmax warps
-  uint64_t* pv_done = bars + 8;     // [2] P half consumed by the tensor core
-  uint64_t* o_full = bars + 10;     // all PV of an item done
+  uint64_t* p_full = bars + 4;      // [2] P half written (over S) by the softmax warps
+  uint64_t* o_full = bars + 10;     // all PV of a kv group done (O complete for the group)
   uint64_t* o_empty = bars + 11;    // O read out by the epilogue warps
   uint64_t* alpha_full = bars + 12; // online softmax: rescale factors of a group published
   uint64_t* corr_done = bars + 13;  // online softmax: O rescaled
@@ -180,9 +182,7 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     mbar_init(q_empty, 1);
     for (int h = 0; h < 2; ++h) {
       mbar_init(&s_full[h], 1);
-      mbar_init(&s_empty[h], 256);
       mbar_init(&p_full[h], 256);
-      mbar_init(&pv_done[h], 1);
     }
     mbar_init(o_full, 1);
     mbar_init(o_empty, 128);
@@ -208,18 +208,17 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0, sc = 0;
-      auto load_rows = [&](const CUtensorMap* m, int img, int bb, int hh, int row0, int rows) {
-        for (int r = 0; r < rows; r += kStageKV) {
-          mbar_wait(&kv_empty[stage], phase ^ 1);
-          uint8_t* dst = sRing + (size_t)stage * C::STAGE_BYTES;
-          mbar_arrive_expect_tx(&kv_full[stage], C::STAGE_BYTES);
+      // one ring stage = up to 128 kv rows (rows past the tensor end are zero-filled by TMA)
+      auto load_half = [&](const CUtensorMap* m, int img, int bb, int hh, int row0) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        uint8_t* dst = sRing + (size_t)stage * C::STAGE_BYTES;
+        mbar_arrive_expect_tx(&kv_full[stage], C::STAGE_BYTES);
 #pragma unroll
-          for (int s = 0; s < C::NSUB; ++s)
-            tma_load_5d(dst + s * C::KV_SUB_BYTES, m, &kv_full[stage], s * C::SUBW, row0 + r, hh, bb, img);
-          if (++stage == C::STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        for (int s = 0; s < C::NSUB; ++s)
+          tma_load_5d(dst + s * C::KV_SUB_BYTES, m, &kv_full[stage], s * C::SUBW, row0, hh, bb, img);
+        if (++stage == C::STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       };
       GroupInfo prev = {};
@@ -233,67 +232,63 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             tma_load_5d(sQ + s * C::Q_SUB_BYTES, &map_q, q_full, s * C::SUBW, G.qt * kBlockQ, G.h, G.b, G.qi);
           ++sc;
         }
-        // the order the MMA warp consumes the ring in: K_A(u), V_A(u-1), K_B(u), V_B(u-1)
-        load_rows(G.self ? &map_ks : &map_k, G.img, G.b, G.h, G.kv0, G.rowsA);
-        if (have_prev) load_rows(prev.self ? &map_vs : &map_v, prev.img, prev.b, prev.h, prev.kv0, prev.rowsA);
-        if (G.rowsB) load_rows(G.self ? &map_ks : &map_k, G.img, G.b, G.h, G.kv0 + kHalfKV, G.rowsB);
-        if (have_prev && prev.rowsB)
-          load_rows(prev.self ? &map_vs : &map_v, prev.img, prev.b, prev.h, prev.kv0 + kHalfKV, prev.rowsB);
+        // the order the MMA warp consumes the ring in: V_A(u-1), K_A(u), V_B(u-1), K_B(u)
+        if (have_prev) load_half(prev.self ? &map_vs : &map_v, prev.img, prev.b, prev.h, prev.kv0);
+        load_half(G.self ? &map_ks : &map_k, G.img, G.b, G.h, G.kv0);
+        if (have_prev && prev.rowsB) load_half(prev.self ? &map_vs : &map_v, prev.img, prev.b, prev.h, prev.kv0 + kHalfKV);
+        if (G.rowsB) load_half(G.self ? &map_ks : &map_k, G.img, G.b, G.h, G.kv0 + kHalfKV);
         prev = G;
         have_prev = true;
       });
       if (have_prev) {
-        load_rows(prev.self ? &map_vs : &map_v, prev.img, prev.b, prev.h, prev.kv0, prev.rowsA);
-        if (prev.rowsB) load_rows(prev.self ? &map_vs : &map_v, prev.img, prev.b, prev.h, prev.kv0 + kHalfKV, prev.rowsB);
+        load_half(prev.self ? &map_vs : &map_v, prev.img, prev.b, prev.h, prev.kv0);
+        if (prev.rowsB) load_half(prev.self ? &map_vs : &map_v, prev.img, prev.b, prev.h, prev.kv0 + kHalfKV);
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
       const uint32_t fmt = kBf16 ? 1u : 0u;
-      const uint32_t idesc_qk = umma_idesc_f16(fmt, kBlockQ, kStageKV, 0, 0);
       const uint32_t idesc_pv = umma_idesc_f16(fmt, kBlockQ, C::D_PAD, 0, 1);
       constexpr uint32_t SBO = 8 * C::SUB_BYTES;  // eight swizzle rows
       // descriptors of the buffer bases; tiles are addressed by adding (byte offset >> 4) to the low word
       const uint64_t q_desc0 = umma_smem_desc(smem_u32(sQ), 16, SBO, C::LAYOUT);
       const uint64_t k_desc0 = umma_smem_desc(smem_u32(sRing), 16, SBO, C::LAYOUT);
       const uint64_t v_desc0 = umma_smem_desc(smem_u32(sRing), C::KV_SUB_BYTES, SBO, C::LAYOUT);
-      const uint64_t p_desc0 = umma_smem_desc(smem_u32(sP), 16, 1024, UMMA_SW128);
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t qk_cnt[2] = {0, 0}, pv_cnt[2] = {0, 0}, sc = 0, items_pv = 0, corr = 0;
+      uint32_t pv_cnt[2] = {0, 0}, sc = 0, items_pv = 0, corr = 0;
       auto advance = [&]() {
         if (++stage == C::STAGES) {
           stage = 0;
           phase ^= 1;
         }
       };
+      // S_h = Q K_h^T: N = the half's kv rows rounded up to 16.  Overwrites the columns PV_h of the previous group
+      // read P from: safe without a barrier because both are issued by this thread, in this order.
       auto issue_qk = [&](const GroupInfo& G, int h) {
         const int rows = h ? G.rowsB : G.rowsA;
-        mbar_wait(&s_empty[h], (qk_cnt[h] & 1) ^ 1);
+        const uint32_t idesc_qk = umma_idesc_f16(fmt, kBlockQ, (uint32_t)((rows + 15) & ~15), 0, 0);
         if (h == 0 && G.first_of_stream) {
           mbar_wait(q_full, sc & 1);
           ++sc;
         }
+        mbar_wait(&kv_full[stage], phase);
         tc_fence_after_sync();
-        for (int r = 0, s = 0; r < rows; r += kStageKV, ++s) {
-          mbar_wait(&kv_full[stage], phase);
-          tc_fence_after_sync();
-          const uint64_t k_desc = k_desc0 + (uint64_t)((stage * C::STAGE_BYTES) >> 4);
-          const uint32_t d_tmem = tmem_base + kTmemS + h * kHalfKV + s * kStageKV;
+        const uint64_t k_desc = k_desc0 + (uint64_t)((stage * C::STAGE_BYTES) >> 4);
+        const uint32_t d_tmem = tmem_base + kTmemS + h * kHalfKV;
 #pragma unroll
-          for (int kc = 0; kc < C::D_PAD / 16; ++kc) {
-            const int sub = kc / C::CPS, off = (kc % C::CPS) * 32;
-            umma_f16_ss(d_tmem, q_desc0 + (uint64_t)((sub * C::Q_SUB_BYTES + off) >> 4),
-                        k_desc + (uint64_t)((sub * C::KV_SUB_BYTES + off) >> 4), idesc_qk, kc > 0 ? 1u : 0u);
-          }
-          umma_commit(&kv_empty[stage]);
-          advance();
+        for (int kc = 0; kc < C::D_PAD / 16; ++kc) {
+          const int sub = kc / C::CPS, off = (kc % C::CPS) * 32;
+          umma_f16_ss(d_tmem, q_desc0 + (uint64_t)((sub * C::Q_SUB_BYTES + off) >> 4),
+                      k_desc + (uint64_t)((sub * C::KV_SUB_BYTES + off) >> 4), idesc_qk, kc > 0 ? 1u : 0u);
         }
+        umma_commit(&kv_empty[stage]);
+        advance();
         umma_commit(&s_full[h]);
-        ++qk_cnt[h];
         if (G.last_of_stream && (h == 1 || G.rowsB == 0)) umma_commit(q_empty);
       };
+      // O (+)= P_h V_h with P_h read from TMEM (written by the softmax warps over S_h)
       auto issue_pv = [&](const GroupInfo& G, int h) {
         const int rows = h ? G.rowsB : G.rowsA;
         mbar_wait(&p_full[h], pv_cnt[h] & 1);
@@ -305,36 +300,32 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             ++corr;
           }
         }
+        mbar_wait(&kv_full[stage], phase);
         tc_fence_after_sync();
-        for (int r = 0, s = 0; r < rows; r += kStageKV, ++s) {
-          mbar_wait(&kv_full[stage], phase);
-          tc_fence_after_sync();
-          const uint64_t v_desc = v_desc0 + (uint64_t)((stage * C::STAGE_BYTES) >> 4);
-          const uint64_t p_desc = p_desc0 + (uint64_t)(((h * 2 + s) * kPSubBytes) >> 4);
-#pragma unroll
-          for (int kk = 0; kk < kStageKV / 16; ++kk) {
-            // A = P[:, 16 kk ...] of this sub-tile (K-major, 128B swizzle); B = V rows 16 kk.. (MN-major)
-            const uint32_t acc = (G.first_of_item && h == 0 && s == 0 && kk == 0) ? 0u : 1u;
-            umma_f16_ss(tmem_base + kTmemO, p_desc + (uint64_t)((kk * 32) >> 4),
-                        v_desc + (uint64_t)((kk * 16 * C::SUB_BYTES) >> 4), idesc_pv, acc);
-          }
-          umma_commit(&kv_empty[stage]);
-          advance();
+        const uint64_t v_desc = v_desc0 + (uint64_t)((stage * C::STAGE_BYTES) >> 4);
+        const int ksteps = (rows + 15) >> 4;
+#pragma unroll 1
+        for (int ks = 0; ks < ksteps; ++ks) {
+          // A = P[:, 16 ks .. 16 ks + 15]: 8 packed TMEM columns; kv columns 64.. of the half sit 64 columns further
+          const uint32_t a_tmem = tmem_base + kTmemS + h * kHalfKV + (ks >> 2) * 64 + (ks & 3) * 8;
+          const uint32_t acc = (G.first_of_item && h == 0 && ks == 0) ? 0u : 1u;
+          umma_f16_ts(tmem_base + kTmemO, a_tmem, v_desc + (uint64_t)((ks * 16 * C::SUB_BYTES) >> 4), idesc_pv, acc);
         }
-        umma_commit(&pv_done[h]);
+        umma_commit(&kv_empty[stage]);
+        advance();
         ++pv_cnt[h];
-        if (G.last_of_item && (h == 1 || G.rowsB == 0)) {
+        if (h == 1 || G.rowsB == 0) {
           umma_commit(o_full);
-          ++items_pv;
+          if (G.last_of_item) ++items_pv;
         }
       };
       GroupInfo prev = {};
       bool have_prev = false;
       for_each_group(p, [&](const GroupInfo& G) {
-        issue_qk(G, 0);
         if (have_prev) issue_pv(prev, 0);
-        if (G.rowsB) issue_qk(G, 1);
+        issue_qk(G, 0);
         if (have_prev && prev.rowsB) issue_pv(prev, 1);
+        if (G.rowsB) issue_qk(G, 1);
         prev = G;
         have_prev = true;
       });
@@ -349,9 +340,7 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const int quad = warp & 3;                   // TMEM lane quadrant this warp may touch
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    const uint32_t s_col = tmem_base + lane_addr + kTmemS + wg * kStageKV;       // + h * 128 + c * 32
-    const uint32_t p_row = smem_u32(sP) + wg * kPSubBytes + row * 128;           // + h * 2 * kPSubBytes
-    const uint32_t swz = (uint32_t)(row & 7);
+    const uint32_t s_col = tmem_base + lane_addr + kTmemS + wg * 64;   // + h * 128 (+ c * 32 for S, + c * 16 for P)
     const float sl2 = p.scale_log2;
     uint32_t cnt[2] = {0, 0}, u = 0, n = 0, corr = 0;
     float m_run = 0.f, l_run = 0.f;
@@ -393,8 +382,8 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       return fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
     };
 
-    // p = exp2(s * scale - M) for 32 columns (chunk c of this thread's 64), written as 16-bit into the swizzled
-    // A tile of the PV product; returns the row-sum contribution
+    // p = exp2(s * scale - M) for 32 columns (chunk c of this thread's 64), written as packed 16-bit pairs over the
+    // first half of the columns just read (the A operand of the PV product); returns the row-sum contribution
     auto exp_chunk = [&](int h, int c, int nv, float M) -> float {
       uint32_t v[32], pk[16];
       tmem_ld_x32(s_col + h * kHalfKV + c * 32, v);
@@ -419,43 +408,27 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         for (int j = 0; j < 32; j += 2) {
           float e0 = fast_exp2(fmaf(__uint_as_float(v[j]), sl2, -M));
           float e1 = fast_exp2(fmaf(__uint_as_float(v[j + 1]), sl2, -M));
-          if (c * 32 + j >= nv) e0 = 0.f;
+          if (c * 32 + j >= nv) e0 = 0.f;      // select, not multiply: stale columns may hold NaN
           if (c * 32 + j + 1 >= nv) e1 = 0.f;
           s0 += e0;
           s1 += e1;
           pk[j >> 1] = pack2<kBf16>(e0, e1);
         }
       }
-      const uint32_t base = p_row + h * (2 * kPSubBytes);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t chunk = (uint32_t)(c * 4 + q) ^ swz;
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + chunk * 16), "r"(pk[4 * q]),
-                     "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
-                     : "memory");
-      }
+      tmem_st_x16(s_col + h * kHalfKV + c * 16, pk);
       return (s0 + s1) + (s2 + s3);
     };
     auto exp_half = [&](int h, int nv, float M) -> float {
-      if (nv <= 0) return 0.f;   // this thread's stage of the half does not exist: the tensor core skips it
+      if (nv <= 0) return 0.f;   // none of this thread's columns exist: the tensor core stops before them
       float s = exp_chunk(h, 0, nv, M);
-      if (nv > 32) {
-        s += exp_chunk(h, 1, nv, M);
-      } else {
-        // columns 32..63 of a stage the tensor core will read: P must be exactly zero there
-        const uint32_t base = p_row + h * (2 * kPSubBytes);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t chunk = (uint32_t)(4 + q) ^ swz;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + chunk * 16), "r"(0u) : "memory");
-        }
-      }
+      // the second chunk only if the PV product reads it: k-steps cover the valid rows rounded up to 16
+      if (nv > 32) s += exp_chunk(h, 1, nv, M);
       return s;
     };
 
     for_each_group(p, [&](const GroupInfo& G) {
-      const int nvA = max(0, min(G.rowsA - wg * kStageKV, kStageKV));
-      const int nvB = max(0, min(G.rowsB - wg * kStageKV, kStageKV));
+      const int nvA = max(0, min(G.rowsA - wg * 64, 64));
+      const int nvB = max(0, min(G.rowsB - wg * 64, 64));
       // ---- pass 1: row maximum over the whole group
       mbar_wait(&s_full[0], cnt[0] & 1);
       tc_fence_after_sync();
@@ -486,29 +459,20 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         ++corr;
       }
       m_run = M;
-      // ---- pass 2, half A
-      mbar_wait(&pv_done[0], (cnt[0] & 1) ^ 1);   // P_A of the previous group has been consumed
+      // ---- pass 2, half A (in place: S_A -> P_A)
       l_run += exp_half(0, nvA, M);
-      if (G.last_of_item && G.rowsB == 0) {
+      if (G.last_of_item && G.rowsB == 0)
         tmem_st_x1(tmem_base + lane_addr + kTmemSum + 2 * (n & 1) + wg, __float_as_uint(l_run));
-        tmem_wait_st();
-      }
-      fence_proxy_async_smem();
+      tmem_wait_st();
       tc_fence_before_sync();
-      mbar_arrive(&s_empty[0]);
       mbar_arrive(&p_full[0]);
       ++cnt[0];
       // ---- pass 2, half B
       if (G.rowsB) {
-        mbar_wait(&pv_done[1], (cnt[1] & 1) ^ 1);
         l_run += exp_half(1, nvB, M);
-        if (G.last_of_item) {
-          tmem_st_x1(tmem_base + lane_addr + kTmemSum + 2 * (n & 1) + wg, __float_as_uint(l_run));
-          tmem_wait_st();
-        }
-        fence_proxy_async_smem();
+        if (G.last_of_item) tmem_st_x1(tmem_base + lane_addr + kTmemSum + 2 * (n & 1) + wg, __float_as_uint(l_run));
+        tmem_wait_st();
         tc_fence_before_sync();
-        mbar_arrive(&s_empty[1]);
         mbar_arrive(&p_full[1]);
         ++cnt[1];
       }
@@ -523,14 +487,14 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const uint32_t o_col = tmem_base + lane_addr + kTmemO;
     const uint32_t os_col = tmem_base + lane_addr + kTmemOs;
     const int tiles = p.B * p.H * p.n_qt;
-    uint32_t n = 0, corr = 0, cntB = 0;
+    uint32_t n = 0, corr = 0, ug = 0;   // items, corrections, kv groups seen
     float ns_tile = 0.f;  // |O_self|^2 of the current stream (meaningful on the reducing thread)
     for_each_group(p, [&](const GroupInfo& G) {
       if (!G.first_of_item) {
         // rescale O by the factors of this group once the previous group's PV has landed (the previous group of an
         // item is always complete, so its last product is PV_B)
         mbar_wait(alpha_full, corr & 1);
-        mbar_wait(&pv_done[1], (cntB - 1) & 1);
+        mbar_wait(o_full, (ug - 1) & 1);
         tc_fence_after_sync();
         const float alpha = __uint_as_float(tmem_ld_x1(tmem_base + lane_addr + kTmemAlpha + (corr & 1)));
         tmem_wait_ld();
@@ -550,12 +514,13 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         mbar_arrive(corr_done);
         ++corr;
       }
-      if (G.rowsB) ++cntB;
+      const uint32_t gpar = ug & 1;
+      ++ug;
       if (!G.last_of_item) return;
 
       const uint32_t par = n & 1;
       const bool row_ok = G.qt * kBlockQ + row < p.Sq;
-      mbar_wait(o_full, par);
+      mbar_wait(o_full, gpar);
       tc_fence_after_sync();
       float inv_l;
       {
@@ -876,10 +841,10 @@ static int launch_attn_d(const AttnLaunch& a, cudaStream_t st) {
   CUtensorMap mq, mks, mvs, mk, mv;
   int rc;
   if ((rc = make_map(&mq, a.q, C::SUBW, kBlockQ)) != DS_OK) return rc;
-  if ((rc = make_map(&mks, a.ks, C::SUBW, kStageKV)) != DS_OK) return rc;
-  if ((rc = make_map(&mvs, a.vs, C::SUBW, kStageKV)) != DS_OK) return rc;
-  if ((rc = make_map(&mk, a.k, C::SUBW, kStageKV)) != DS_OK) return rc;
-  if ((rc = make_map(&mv, a.v, C::SUBW, kStageKV)) != DS_OK) return rc;
+  if ((rc = make_map(&mks, a.ks, C::SUBW, kHalfKV)) != DS_OK) return rc;
+  if ((rc = make_map(&mvs, a.vs, C::SUBW, kHalfKV)) != DS_OK) return rc;
+  if ((rc = make_map(&mk, a.k, C::SUBW, kHalfKV)) != DS_OK) return rc;
+  if ((rc = make_map(&mv, a.v, C::SUBW, kHalfKV)) != DS_OK) return rc;
   const int64_t n_streams = (int64_t)a.p.n_groups * a.p.B * a.p.H * a.p.n_qt;
   int grid = sm_count();
   if (n_streams < grid) grid = (int)n_streams;
