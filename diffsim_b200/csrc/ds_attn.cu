@@ -3,11 +3,11 @@
 // One persistent, warp-specialised CTA per SM:
 //
 //   warp 0        TMA producer   Q tile (per stream) and a ring of 128-row K / V stages
-//   warp 1        MMA issuer     tcgen05.mma: S = Q K^T (fp32, TMEM), O (+)= P V (fp32, TMEM; P read from TMEM)
-//   warp 2        TMEM allocator
-//   warps 4-11    softmax        256 threads; thread = (q row, 64 of the 128 kv columns of an S half);
+//   warp 1        MMA issuer     tcgen05.mma: S = Q K^T (fp32, TMEM), O (+)= P V (fp32, TMEM; P read from TMEM);
+//                                also allocates / frees TMEM
+//   warps 6-21    softmax        512 threads; thread = (q row, 32 of the 128 kv columns of an S half);
 //                                S (TMEM) -> exp2 -> P (16-bit, written IN PLACE over S: the A operand of PV)
-//   warps 12-15   epilogue       O (TMEM) -> 1/l ->
+//   warps 2-5     epilogue       O (TMEM) -> 1/l ->
 //                                  self item : O_self rounded to the input dtype, kept on chip (TMEM), |O_self|^2
 //                                  cross item: dot(O_cross,O_self), |O_cross|^2 or sum (O_cross-O_self)^2
 //                                  store mode: write O to global (the SDPA replacement)
@@ -44,17 +44,17 @@ namespace ds {
 
 enum : int { ATTN_MODE_COS = 0, ATTN_MODE_MSE = 1, ATTN_MODE_STORE = 2 };
 
-constexpr int kAttnThreads = 512;
+constexpr int kAttnThreads = 704;   // 22 warps: producer, MMA, 4 epilogue, 16 softmax
 constexpr int kBlockQ = 128;     // q rows per tile == TMEM lanes
 constexpr int kHalfKV = 128;     // kv rows per S half == per ring stage
 constexpr int kGroupKV = 256;    // kv rows per softmax group (two halves)
 constexpr int kTmemCols = 512;
-constexpr int kTmemS = 0;        // S_A: columns [0,128), S_B: [128,256); P of the thread's 64 kv columns
-                                 // overwrites the first 32 of its own 64 S columns
+constexpr int kTmemS = 0;        // S_A: columns [0,128), S_B: [128,256); P of the thread's 32 kv columns
+                                 // overwrites the first 16 of its own 32 S columns
 constexpr int kTmemO = 256;      // O: [256, 256 + D_PAD)
 constexpr int kTmemOs = 416;     // O_self, packed 16-bit: [416, 416 + D_PAD/2)
-constexpr int kTmemSum = 496;    // row sums: 496 + 2 * (item parity) + (column half of the thread)
-constexpr int kTmemAlpha = 500;  // online-softmax rescale factors: 500 + (correction parity)
+constexpr int kTmemSum = 496;    // row sums: 496 + 4 * (item parity) + (column quarter of the thread)
+constexpr int kTmemAlpha = 504;  // online-softmax rescale factors: 504 + (correction parity)
 
 template <int D>
 struct AttnCfg {
@@ -68,7 +68,7 @@ struct AttnCfg {
   static constexpr int Q_BYTES = NSUB * Q_SUB_BYTES;
   static constexpr int KV_SUB_BYTES = kHalfKV * SUB_BYTES;
   static constexpr int STAGE_BYTES = NSUB * KV_SUB_BYTES;
-  static constexpr int MISC_BYTES = 2048 /*max exchange*/ + 128 /*epilogue reduce*/ + 512 /*barriers*/;
+  static constexpr int MISC_BYTES = 4096 /*max exchange*/ + 128 /*epilogue reduce*/ + 512 /*barriers*/;
   static constexpr int kMaxSmem = 232448;
   static constexpr int STAGES_RAW = (kMaxSmem - Q_BYTES - MISC_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 12 ? 12 : STAGES_RAW;
@@ -148,8 +148,8 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sRing = sQ + C::Q_BYTES;
-  float* sMax = reinterpret_cast<float*>(sRing + C::STAGES * C::STAGE_BYTES);  // [2 parity][2 col half][128]
-  float* sRed = sMax + 512;                                                    // [2 parity][4 warps][4]
+  float* sMax = reinterpret_cast<float*>(sRing + C::STAGES * C::STAGE_BYTES);  // [2 parity][4 col quarter][128]
+  float* sRed = sMax + 1024;                                                   // [2 parity][4 warps][4]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 32);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
@@ -182,7 +182,7 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     mbar_init(q_empty, 1);
     for (int h = 0; h < 2; ++h) {
       mbar_init(&s_full[h], 1);
-      mbar_init(&p_full[h], 256);
+      mbar_init(&p_full[h], 512);
     }
     mbar_init(o_full, 1);
     mbar_init(o_empty, 128);
@@ -194,7 +194,7 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
     fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == 1) {
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
@@ -257,7 +257,7 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const uint64_t v_desc0 = umma_smem_desc(smem_u32(sRing), C::KV_SUB_BYTES, SBO, C::LAYOUT);
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t pv_cnt[2] = {0, 0}, sc = 0, items_pv = 0, corr = 0;
+      uint32_t pv_cntA = 0, pv_cntB = 0, sc = 0, items_pv = 0, corr = 0;
       auto advance = [&]() {
         if (++stage == C::STAGES) {
           stage = 0;
@@ -291,7 +291,7 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       // O (+)= P_h V_h with P_h read from TMEM (written by the softmax warps over S_h)
       auto issue_pv = [&](const GroupInfo& G, int h) {
         const int rows = h ? G.rowsB : G.rowsA;
-        mbar_wait(&p_full[h], pv_cnt[h] & 1);
+        mbar_wait(&p_full[h], (h ? pv_cntB : pv_cntA) & 1);
         if (h == 0) {
           if (G.first_of_item) {
             mbar_wait(o_empty, (items_pv & 1) ^ 1);
@@ -306,14 +306,14 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const int ksteps = (rows + 15) >> 4;
 #pragma unroll 1
         for (int ks = 0; ks < ksteps; ++ks) {
-          // A = P[:, 16 ks .. 16 ks + 15]: 8 packed TMEM columns; kv columns 64.. of the half sit 64 columns further
-          const uint32_t a_tmem = tmem_base + kTmemS + h * kHalfKV + (ks >> 2) * 64 + (ks & 3) * 8;
+          // A = P[:, 16 ks .. 16 ks + 15]: 8 packed TMEM columns inside the 32-column quarter the kv columns belong to
+          const uint32_t a_tmem = tmem_base + kTmemS + h * kHalfKV + (ks >> 1) * 32 + (ks & 1) * 8;
           const uint32_t acc = (G.first_of_item && h == 0 && ks == 0) ? 0u : 1u;
           umma_f16_ts(tmem_base + kTmemO, a_tmem, v_desc + (uint64_t)((ks * 16 * C::SUB_BYTES) >> 4), idesc_pv, acc);
         }
         umma_commit(&kv_empty[stage]);
         advance();
-        ++pv_cnt[h];
+        if (h) ++pv_cntB; else ++pv_cntA;
         if (h == 1 || G.rowsB == 0) {
           umma_commit(o_full);
           if (G.last_of_item) ++items_pv;
@@ -334,62 +334,49 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if (prev.rowsB) issue_pv(prev, 1);
       }
     }
-  } else if (warp >= 4 && warp < 12) {
+  } else if (warp >= 6) {
     // ------------------------------------------------------------------ softmax
-    const int wg = (warp - 4) >> 2;              // which 64 columns of each S half
+    const int qtr = (warp - 6) >> 2;             // which 32 columns of each S half
     const int quad = warp & 3;                   // TMEM lane quadrant this warp may touch
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    const uint32_t s_col = tmem_base + lane_addr + kTmemS + wg * 64;   // + h * 128 (+ c * 32 for S, + c * 16 for P)
+    const uint32_t s_col = tmem_base + lane_addr + kTmemS + qtr * 32;   // + h * 128; P goes to the first 16 of the 32
     const float sl2 = p.scale_log2;
-    uint32_t cnt[2] = {0, 0}, u = 0, n = 0, corr = 0;
+    uint32_t cntA = 0, cntB = 0, u = 0, n = 0, corr = 0;
     float m_run = 0.f, l_run = 0.f;
 
-    // maximum of the nv valid columns (of this thread's 64) of S half h
+    // maximum of the nv valid columns (of this thread's 32) of S half h
     auto row_max = [&](int h, int nv, float m) -> float {
       if (nv <= 0) return m;
-      uint32_t v0[32], v1[32];
-      tmem_ld_x32(s_col + h * kHalfKV, v0);
-      if (nv > 32) tmem_ld_x32(s_col + h * kHalfKV + 32, v1);
+      uint32_t v[32];
+      tmem_ld_x32(s_col + h * kHalfKV, v);
       tmem_wait_ld();
       float a0 = m, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
-      if (nv >= 32) {
+      if (nv == 32) {
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
-          a0 = fmaxf(a0, fmaxf(__uint_as_float(v0[j]), __uint_as_float(v0[j + 1])));
-          a1 = fmaxf(a1, fmaxf(__uint_as_float(v0[j + 2]), __uint_as_float(v0[j + 3])));
-          a2 = fmaxf(a2, fmaxf(__uint_as_float(v0[j + 4]), __uint_as_float(v0[j + 5])));
-          a3 = fmaxf(a3, fmaxf(__uint_as_float(v0[j + 6]), __uint_as_float(v0[j + 7])));
+          a0 = fmaxf(a0, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+          a1 = fmaxf(a1, fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+          a2 = fmaxf(a2, fmaxf(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])));
+          a3 = fmaxf(a3, fmaxf(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])));
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (j < nv) a0 = fmaxf(a0, __uint_as_float(v0[j]));
-      }
-      if (nv == 64) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          a0 = fmaxf(a0, fmaxf(__uint_as_float(v1[j]), __uint_as_float(v1[j + 1])));
-          a1 = fmaxf(a1, fmaxf(__uint_as_float(v1[j + 2]), __uint_as_float(v1[j + 3])));
-          a2 = fmaxf(a2, fmaxf(__uint_as_float(v1[j + 4]), __uint_as_float(v1[j + 5])));
-          a3 = fmaxf(a3, fmaxf(__uint_as_float(v1[j + 6]), __uint_as_float(v1[j + 7])));
-        }
-      } else if (nv > 32) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (32 + j < nv) a1 = fmaxf(a1, __uint_as_float(v1[j]));
+          if (j < nv) a0 = fmaxf(a0, __uint_as_float(v[j]));
       }
       return fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
     };
 
-    // p = exp2(s * scale - M) for 32 columns (chunk c of this thread's 64), written as packed 16-bit pairs over the
-    // first half of the columns just read (the A operand of the PV product); returns the row-sum contribution
-    auto exp_chunk = [&](int h, int c, int nv, float M) -> float {
+    // p = exp2(s * scale - M) for this thread's 32 columns of half h, written as packed 16-bit pairs over the first
+    // half of the columns just read (the A operand of the PV product); returns the row-sum contribution
+    auto exp_half = [&](int h, int nv, float M) -> float {
+      if (nv <= 0) return 0.f;   // none of this thread's columns exist: the tensor core stops before them
       uint32_t v[32], pk[16];
-      tmem_ld_x32(s_col + h * kHalfKV + c * 32, v);
+      tmem_ld_x32(s_col + h * kHalfKV, v);
       tmem_wait_ld();
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      if (c * 32 + 32 <= nv) {
+      if (nv == 32) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const float e0 = fast_exp2(fmaf(__uint_as_float(v[j]), sl2, -M));
@@ -408,41 +395,33 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         for (int j = 0; j < 32; j += 2) {
           float e0 = fast_exp2(fmaf(__uint_as_float(v[j]), sl2, -M));
           float e1 = fast_exp2(fmaf(__uint_as_float(v[j + 1]), sl2, -M));
-          if (c * 32 + j >= nv) e0 = 0.f;      // select, not multiply: stale columns may hold NaN
-          if (c * 32 + j + 1 >= nv) e1 = 0.f;
+          if (j >= nv) e0 = 0.f;      // select, not multiply: stale columns may hold NaN
+          if (j + 1 >= nv) e1 = 0.f;
           s0 += e0;
           s1 += e1;
           pk[j >> 1] = pack2<kBf16>(e0, e1);
         }
       }
-      tmem_st_x16(s_col + h * kHalfKV + c * 16, pk);
+      tmem_st_x16(s_col + h * kHalfKV, pk);
       return (s0 + s1) + (s2 + s3);
-    };
-    auto exp_half = [&](int h, int nv, float M) -> float {
-      if (nv <= 0) return 0.f;   // none of this thread's columns exist: the tensor core stops before them
-      float s = exp_chunk(h, 0, nv, M);
-      // the second chunk only if the PV product reads it: k-steps cover the valid rows rounded up to 16
-      if (nv > 32) s += exp_chunk(h, 1, nv, M);
-      return s;
     };
 
     for_each_group(p, [&](const GroupInfo& G) {
-      const int nvA = max(0, min(G.rowsA - wg * 64, 64));
-      const int nvB = max(0, min(G.rowsB - wg * 64, 64));
+      const int nvA = max(0, min(G.rowsA - qtr * 32, 32)), nvB = max(0, min(G.rowsB - qtr * 32, 32));
+      const int n_half = G.rowsB ? 2 : 1;
       // ---- pass 1: row maximum over the whole group
-      mbar_wait(&s_full[0], cnt[0] & 1);
-      tc_fence_after_sync();
-      float m = row_max(0, nvA, -INFINITY);
-      if (G.rowsB) {
-        mbar_wait(&s_full[1], cnt[1] & 1);
+      float m = -INFINITY;
+#pragma unroll 1
+      for (int h = 0; h < n_half; ++h) {
+        mbar_wait(&s_full[h], (h ? cntB : cntA) & 1);
         tc_fence_after_sync();
-        m = row_max(1, nvB, m);
+        m = row_max(h, h ? nvB : nvA, m);
       }
       m *= sl2;
-      float* mx = sMax + (u & 1) * 256;
-      mx[wg * 128 + row] = m;
-      named_bar_sync(1, 256);
-      float M = fmaxf(m, mx[(wg ^ 1) * 128 + row]);
+      float* mx = sMax + (u & 1) * 512;
+      mx[qtr * 128 + row] = m;
+      named_bar_sync(1, 512);
+      float M = fmaxf(fmaxf(mx[row], mx[128 + row]), fmaxf(mx[256 + row], mx[384 + row]));
       if (G.first_of_item) {
         l_run = 0.f;
       } else {
@@ -450,7 +429,7 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         M = fmaxf(m_run, M);
         const float alpha = fast_exp2(m_run - M);
         l_run *= alpha;
-        if (wg == 0) {
+        if (qtr == 0) {
           tmem_st_x1(tmem_base + lane_addr + kTmemAlpha + (corr & 1), __float_as_uint(alpha));
           tmem_wait_st();
           tc_fence_before_sync();
@@ -459,28 +438,22 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         ++corr;
       }
       m_run = M;
-      // ---- pass 2, half A (in place: S_A -> P_A)
-      l_run += exp_half(0, nvA, M);
-      if (G.last_of_item && G.rowsB == 0)
-        tmem_st_x1(tmem_base + lane_addr + kTmemSum + 2 * (n & 1) + wg, __float_as_uint(l_run));
-      tmem_wait_st();
-      tc_fence_before_sync();
-      mbar_arrive(&p_full[0]);
-      ++cnt[0];
-      // ---- pass 2, half B
-      if (G.rowsB) {
-        l_run += exp_half(1, nvB, M);
-        if (G.last_of_item) tmem_st_x1(tmem_base + lane_addr + kTmemSum + 2 * (n & 1) + wg, __float_as_uint(l_run));
+      // ---- pass 2 (in place: S_h -> P_h), half A then half B
+#pragma unroll 1
+      for (int h = 0; h < n_half; ++h) {
+        l_run += exp_half(h, h ? nvB : nvA, M);
+        if (G.last_of_item && h == n_half - 1)
+          tmem_st_x1(tmem_base + lane_addr + kTmemSum + 4 * (n & 1) + qtr, __float_as_uint(l_run));
         tmem_wait_st();
         tc_fence_before_sync();
-        mbar_arrive(&p_full[1]);
-        ++cnt[1];
+        mbar_arrive(&p_full[h]);
+        if (h) ++cntB; else ++cntA;
       }
       if (G.last_of_item) ++n;
       ++u;
     });
-  } else if (warp >= 12) {
-    // ------------------------------------------------------------------ epilogue / correction
+  } else {
+    // ------------------------------------------------------------------ epilogue / correction (warps 2-5)
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
@@ -524,13 +497,13 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       tc_fence_after_sync();
       float inv_l;
       {
-        uint32_t s0, s1;
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];"
-                     : "=r"(s0), "=r"(s1)
-                     : "r"(tmem_base + lane_addr + kTmemSum + 2 * par)
+        uint32_t s0, s1, s2, s3;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(s0), "=r"(s1), "=r"(s2), "=r"(s3)
+                     : "r"(tmem_base + lane_addr + kTmemSum + 4 * par)
                      : "memory");
         tmem_wait_ld();
-        inv_l = 1.0f / (__uint_as_float(s0) + __uint_as_float(s1));
+        inv_l = 1.0f / ((__uint_as_float(s0) + __uint_as_float(s1)) + (__uint_as_float(s2) + __uint_as_float(s3)));
       }
       float acc0 = 0.f, acc1 = 0.f;   // cosine: dot / |Oc|^2 (cross), |Os|^2 (self); mse: sum of squared differences
       uint8_t* out_row = nullptr;
@@ -569,11 +542,12 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             pk[j] = pack2<kBf16>(__uint_as_float(v[2 * j]) * inv_l, __uint_as_float(v[2 * j + 1]) * inv_l);
           tmem_st_x8(os_col + c * 8, pk);
           if constexpr (MODE == ATTN_MODE_COS) {
+            // |O_self|^2 from the unrounded values, normalised once per row below (differs from the norm of the
+            // rounded vector by O(eps^2))
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float2 o = unpack2<kBf16>(pk[j]);
-              acc0 = fmaf(o.x, o.x, acc0);
-              acc1 = fmaf(o.y, o.y, acc1);
+            for (int j = 0; j < 16; j += 2) {
+              acc0 = fmaf(__uint_as_float(v[j]), __uint_as_float(v[j]), acc0);
+              acc1 = fmaf(__uint_as_float(v[j + 1]), __uint_as_float(v[j + 1]), acc1);
             }
           }
         } else {
@@ -607,7 +581,7 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if (G.self) tmem_wait_st();
         float r0, r1;   // cross: (dot, |Oc|^2) or (sq, 0); self: (|Os|^2, 0)
         if (G.self) {
-          r0 = acc0 + acc1;
+          r0 = (acc0 + acc1) * inv_l * inv_l;
           r1 = 0.f;
         } else if constexpr (MODE == ATTN_MODE_COS) {
           r0 = acc0 * inv_l;
@@ -643,7 +617,7 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // dir[t] from the per-tile partials, tiles added in index order (deterministic)
