@@ -10,7 +10,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libdiffsim_b200.so")
+# DIFFSIM_B200_LIB selects another build of the same library (e.g. the -DDS_TRACE debug build)
+LIB_PATH = os.environ.get("DIFFSIM_B200_LIB") or os.path.join(_HERE, "_lib", "libdiffsim_b200.so")
 
 DS_OK = 0
 DS_ERR_INVALID, DS_ERR_UNSUPPORTED, DS_ERR_CUDA, DS_ERR_WORKSPACE = -1, -2, -3, -4
@@ -50,6 +51,7 @@ PROTOTYPES = {
     "ds_device_ok": (_i, []),
     "ds_profile_enable": (_i, [_i]),
     "ds_profile_collect": (_i, [C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "ds_debug_set_trace": (_i, [_vp, _i]),
     "ds_attn_fwd": (_i, [Tensor4, Tensor4, Tensor4, _f, Tensor4, _vp, _sz, _vp]),
     "ds_attn_fwd_workspace_bytes": (_sz, [Tensor4, Tensor4]),
     "ds_aas_groups": (_i, [Tensor5, Tensor5, Tensor5, Tensor5, Tensor5, _vp, _vp, _i64, _vp, _i64, _f, _i, _vp, _vp, _sz, _vp]),

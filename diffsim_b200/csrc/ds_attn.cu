@@ -5,13 +5,15 @@
 //   warp 0        TMA producer   Q tile (per stream) and a ring of 128-row K / V stages
 //   warp 1        MMA issuer     tcgen05.mma: S = Q K^T (fp32, TMEM), O (+)= P V (fp32, TMEM; P read from TMEM);
 //                                also allocates / frees TMEM
-//   warps 6-21    softmax        512 threads; thread = (q row, 32 of the 128 kv columns of an S half);
+//   warps 10-25   softmax        512 threads; thread = (q row, 32 of the 128 kv columns of an S half);
 //                                S (TMEM) -> exp2 -> P (16-bit, written IN PLACE over S: the A operand of PV)
-//   warps 2-5     epilogue       O (TMEM) -> 1/l ->
+//   warps 2-9     epilogue       256 threads; thread = (q row, half of the head dim); O (TMEM) -> 1/l ->
 //                                  self item : O_self rounded to the input dtype, kept on chip (TMEM), |O_self|^2
 //                                  cross item: dot(O_cross,O_self), |O_cross|^2 or sum (O_cross-O_self)^2
 //                                  store mode: write O to global (the SDPA replacement)
-//                                and, for kv lengths > 256, the online-softmax rescale of O between groups
+//
+// (O is single-buffered in TMEM -- 2 x 160 columns do not fit next to S -- so the time the epilogue needs to drain
+// it sits on the critical path of the next item's first PV: hence eight epilogue warps, two per scheduler.)
 //
 // Work decomposition.  A "stream" is (group, b, h, 128-row q tile): the Q tile stays resident while the kv
 // images of the group ("items") stream through; the first item of a group is the query image's own K/V (the
@@ -25,10 +27,12 @@
 // softmax warps overwrite S in TMEM with 16-bit P and the PV MMA takes its A operand from TMEM), and O_self
 // lives in TMEM as well.  Shared memory then carries only TMA writes + one read of K and V + two reads of Q.
 //
-// Softmax.  The row maximum is taken over the whole group before any exponential (exact two-pass softmax:
-// for kv <= 256 -- SD-1.5 up_blocks[0], DiT -- there is exactly one group and no rescaling anywhere); across
-// groups the running maximum / sum are carried in registers and O is rescaled in TMEM by the epilogue warps
-// (skipped per warp when no row maximum moved).
+// Softmax.  Online over 128-column halves with a LAZY running maximum: the first half of an item fixes the
+// reference maximum m of every row; a later half only moves m (and rescales O and the running sum) when some
+// row of the tile exceeds m by more than 2^8 -- otherwise p = exp2(s - m) is simply allowed to be as large as
+// 256, which 16-bit P and fp32 sums hold without loss.  The result is the exact softmax either way (any common
+// offset cancels in O / l).  The rare rescale is done by the first-quarter softmax warps themselves before they
+// release P, so the common path has no extra barrier and half A never waits for half B.
 //
 // Pipeline.  The MMA warp issues, in this fixed order, PV_A(u), QK_A(u+1), PV_B(u), QK_B(u+1): tcgen05 ops of
 // one thread execute in issue order, so QK_A(u+1) may overwrite the columns PV_A(u) reads P from without any
@@ -44,7 +48,10 @@ namespace ds {
 
 enum : int { ATTN_MODE_COS = 0, ATTN_MODE_MSE = 1, ATTN_MODE_STORE = 2 };
 
-constexpr int kAttnThreads = 704;   // 22 warps: producer, MMA, 4 epilogue, 16 softmax
+constexpr int kAttnThreads = 832;   // 26 warps: producer, MMA, 8 epilogue, 16 softmax
+constexpr int kWarpProducer = 0;
+constexpr int kWarpMma = 1;
+constexpr int kWarpSoftmax0 = 10;
 constexpr int kBlockQ = 128;     // q rows per tile == TMEM lanes
 constexpr int kHalfKV = 128;     // kv rows per S half == per ring stage
 constexpr int kGroupKV = 256;    // kv rows per softmax group (two halves)
@@ -54,7 +61,6 @@ constexpr int kTmemS = 0;        // S_A: columns [0,128), S_B: [128,256); P of t
 constexpr int kTmemO = 256;      // O: [256, 256 + D_PAD)
 constexpr int kTmemOs = 416;     // O_self, packed 16-bit: [416, 416 + D_PAD/2)
 constexpr int kTmemSum = 496;    // row sums: 496 + 4 * (item parity) + (column quarter of the thread)
-constexpr int kTmemAlpha = 504;  // online-softmax rescale factors: 504 + (correction parity)
 
 template <int D>
 struct AttnCfg {
@@ -93,7 +99,23 @@ struct AttnParams {
   // store-mode output: element strides of (b, h, s); the innermost stride is 1
   void* out;
   int64_t out_sb, out_sh, out_ss;
+  // debug timeline (ds_debug_set_trace; compiled in only with -DDS_TRACE): [8 slots][cap] of (tag << 48 | clock)
+  unsigned long long* trace;
+  int trace_cap;
+  unsigned long long* cycles;   // optional: CTA 0 stores its elapsed SM clocks here (ds_debug_set_trace(buf, cap): buf[8*cap])
 };
+
+#ifdef DS_TRACE
+#define DS_TRACE_DECL(slot) int _tr_n = 0; const int _tr_slot = (slot); const bool _tr_on = p.trace && blockIdx.x == 0;
+#define DS_TRACE_EV(tag)                                                                                   \
+  do {                                                                                                     \
+    if (_tr_on && _tr_n < p.trace_cap)                                                                     \
+      p.trace[(size_t)_tr_slot * p.trace_cap + _tr_n++] = ((unsigned long long)(tag) << 48) | (clock64() & 0xFFFFFFFFFFFFull); \
+  } while (0)
+#else
+#define DS_TRACE_DECL(slot)
+#define DS_TRACE_EV(tag)
+#endif
 
 // One kv group of one item of one stream, as every warp role enumerates them (identically).
 struct GroupInfo {
@@ -155,29 +177,29 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   uint64_t* q_empty = bars + 1;
   uint64_t* s_full = bars + 2;      // [2] S half written by the tensor core
   uint64_t* p_full = bars + 4;      // [2] P half written (over S) by the softmax warps
-  uint64_t* o_full = bars + 10;     // all PV of a kv group done (O complete for the group)
+  uint64_t* o_full = bars + 10;     // all PV of an item done: O complete (one phase per item)
+  uint64_t* pv_half = bars + 12;    // PV of one half done (one phase per half; only the rare rescale path waits on it)
   uint64_t* o_empty = bars + 11;    // O read out by the epilogue warps
-  uint64_t* alpha_full = bars + 12; // online softmax: rescale factors of a group published
-  uint64_t* corr_done = bars + 13;  // online softmax: O rescaled
   uint64_t* kv_full = bars + 16;
   uint64_t* kv_empty = bars + 16 + C::STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16 + 2 * C::STAGES);
   static_assert((16 + 2 * C::STAGES) * 8 + 16 <= 512, "barrier area");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long clk_start = clock64();
 
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("diffsim_b200: dynamic shared memory is not 1024-byte aligned\n");
     __trap();
   }
-  if (warp == 0 && lane == 0) {
+  if (warp == kWarpProducer && lane == 0) {
     tma_prefetch_desc(&map_q);
     tma_prefetch_desc(&map_ks);
     tma_prefetch_desc(&map_vs);
     tma_prefetch_desc(&map_k);
     tma_prefetch_desc(&map_v);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == kWarpMma && lane == 0) {
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
     for (int h = 0; h < 2; ++h) {
@@ -185,16 +207,15 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       mbar_init(&p_full[h], 512);
     }
     mbar_init(o_full, 1);
-    mbar_init(o_empty, 128);
-    mbar_init(alpha_full, 128);
-    mbar_init(corr_done, 128);
+    mbar_init(pv_half, 1);
+    mbar_init(o_empty, 256);
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == kWarpMma) {
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
@@ -203,14 +224,17 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == kWarpProducer) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0, sc = 0;
       // one ring stage = up to 128 kv rows (rows past the tensor end are zero-filled by TMA)
+      DS_TRACE_DECL(0)
       auto load_half = [&](const CUtensorMap* m, int img, int bb, int hh, int row0) {
+        DS_TRACE_EV(1);
         mbar_wait(&kv_empty[stage], phase ^ 1);
+        DS_TRACE_EV(2);
         uint8_t* dst = sRing + (size_t)stage * C::STAGE_BYTES;
         mbar_arrive_expect_tx(&kv_full[stage], C::STAGE_BYTES);
 #pragma unroll
@@ -224,6 +248,10 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       GroupInfo prev = {};
       bool have_prev = false;
       for_each_group(p, [&](const GroupInfo& G) {
+        // the order the MMA warp consumes the ring in: V_A(u-1), K_A(u), V_B(u-1), K_B(u).  V_A(u-1) goes first, BEFORE
+        // the wait for the Q buffer: at a stream boundary that wait lasts until the old stream's last QK has completed,
+        // and PV_A(u-1) must not queue behind it.
+        if (have_prev) load_half(prev.self ? &map_vs : &map_v, prev.img, prev.b, prev.h, prev.kv0);
         if (G.first_of_stream) {
           mbar_wait(q_empty, (sc & 1) ^ 1);
           mbar_arrive_expect_tx(q_full, C::Q_BYTES);
@@ -232,8 +260,6 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             tma_load_5d(sQ + s * C::Q_SUB_BYTES, &map_q, q_full, s * C::SUBW, G.qt * kBlockQ, G.h, G.b, G.qi);
           ++sc;
         }
-        // the order the MMA warp consumes the ring in: V_A(u-1), K_A(u), V_B(u-1), K_B(u)
-        if (have_prev) load_half(prev.self ? &map_vs : &map_v, prev.img, prev.b, prev.h, prev.kv0);
         load_half(G.self ? &map_ks : &map_k, G.img, G.b, G.h, G.kv0);
         if (have_prev && prev.rowsB) load_half(prev.self ? &map_vs : &map_v, prev.img, prev.b, prev.h, prev.kv0 + kHalfKV);
         if (G.rowsB) load_half(G.self ? &map_ks : &map_k, G.img, G.b, G.h, G.kv0 + kHalfKV);
@@ -245,7 +271,7 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if (prev.rowsB) load_half(prev.self ? &map_vs : &map_v, prev.img, prev.b, prev.h, prev.kv0 + kHalfKV);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kWarpMma) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
       const uint32_t fmt = kBf16 ? 1u : 0u;
@@ -257,7 +283,7 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const uint64_t v_desc0 = umma_smem_desc(smem_u32(sRing), C::KV_SUB_BYTES, SBO, C::LAYOUT);
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t pv_cntA = 0, pv_cntB = 0, sc = 0, items_pv = 0, corr = 0;
+      uint32_t pv_cntA = 0, pv_cntB = 0, sc = 0, items_pv = 0;
       auto advance = [&]() {
         if (++stage == C::STAGES) {
           stage = 0;
@@ -266,14 +292,17 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       };
       // S_h = Q K_h^T: N = the half's kv rows rounded up to 16.  Overwrites the columns PV_h of the previous group
       // read P from: safe without a barrier because both are issued by this thread, in this order.
+      DS_TRACE_DECL(1)
       auto issue_qk = [&](const GroupInfo& G, int h) {
         const int rows = h ? G.rowsB : G.rowsA;
+        DS_TRACE_EV(10 + h);
         const uint32_t idesc_qk = umma_idesc_f16(fmt, kBlockQ, (uint32_t)((rows + 15) & ~15), 0, 0);
         if (h == 0 && G.first_of_stream) {
           mbar_wait(q_full, sc & 1);
           ++sc;
         }
         mbar_wait(&kv_full[stage], phase);
+        DS_TRACE_EV(12 + h);
         tc_fence_after_sync();
         const uint64_t k_desc = k_desc0 + (uint64_t)((stage * C::STAGE_BYTES) >> 4);
         const uint32_t d_tmem = tmem_base + kTmemS + h * kHalfKV;
@@ -286,21 +315,18 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         umma_commit(&kv_empty[stage]);
         advance();
         umma_commit(&s_full[h]);
+        DS_TRACE_EV(14 + h);
         if (G.last_of_stream && (h == 1 || G.rowsB == 0)) umma_commit(q_empty);
       };
       // O (+)= P_h V_h with P_h read from TMEM (written by the softmax warps over S_h)
       auto issue_pv = [&](const GroupInfo& G, int h) {
         const int rows = h ? G.rowsB : G.rowsA;
+        DS_TRACE_EV(20 + h);
         mbar_wait(&p_full[h], (h ? pv_cntB : pv_cntA) & 1);
-        if (h == 0) {
-          if (G.first_of_item) {
-            mbar_wait(o_empty, (items_pv & 1) ^ 1);
-          } else {
-            mbar_wait(corr_done, corr & 1);
-            ++corr;
-          }
-        }
+        DS_TRACE_EV(22 + h);
+        if (h == 0 && G.first_of_item) mbar_wait(o_empty, (items_pv & 1) ^ 1);
         mbar_wait(&kv_full[stage], phase);
+        DS_TRACE_EV(24 + h);
         tc_fence_after_sync();
         const uint64_t v_desc = v_desc0 + (uint64_t)((stage * C::STAGE_BYTES) >> 4);
         const int ksteps = (rows + 15) >> 4;
@@ -314,9 +340,11 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         umma_commit(&kv_empty[stage]);
         advance();
         if (h) ++pv_cntB; else ++pv_cntA;
-        if (h == 1 || G.rowsB == 0) {
+        umma_commit(pv_half);
+        DS_TRACE_EV(26 + h);
+        if (G.last_of_item && (h == 1 || G.rowsB == 0)) {
           umma_commit(o_full);
-          if (G.last_of_item) ++items_pv;
+          ++items_pv;
         }
       };
       GroupInfo prev = {};
@@ -334,166 +362,164 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if (prev.rowsB) issue_pv(prev, 1);
       }
     }
-  } else if (warp >= 6) {
+  } else if (warp >= kWarpSoftmax0) {
     // ------------------------------------------------------------------ softmax
-    const int qtr = (warp - 6) >> 2;             // which 32 columns of each S half
+    const int qtr = (warp - kWarpSoftmax0) >> 2;            // which 32 columns of each S half
     const int quad = warp & 3;                   // TMEM lane quadrant this warp may touch
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const uint32_t s_col = tmem_base + lane_addr + kTmemS + qtr * 32;   // + h * 128; P goes to the first 16 of the 32
+    const uint32_t o_col = tmem_base + lane_addr + kTmemO;
     const float sl2 = p.scale_log2;
-    uint32_t cntA = 0, cntB = 0, u = 0, n = 0, corr = 0;
+    uint32_t cntA = 0, cntB = 0, w = 0, n = 0;   // halves A / B seen, half-steps, items
     float m_run = 0.f, l_run = 0.f;
-
-    // maximum of the nv valid columns (of this thread's 32) of S half h
-    auto row_max = [&](int h, int nv, float m) -> float {
-      if (nv <= 0) return m;
-      uint32_t v[32];
-      tmem_ld_x32(s_col + h * kHalfKV, v);
-      tmem_wait_ld();
-      float a0 = m, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
-      if (nv == 32) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          a0 = fmaxf(a0, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
-          a1 = fmaxf(a1, fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
-          a2 = fmaxf(a2, fmaxf(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])));
-          a3 = fmaxf(a3, fmaxf(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])));
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < nv) a0 = fmaxf(a0, __uint_as_float(v[j]));
-      }
-      return fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
-    };
-
-    // p = exp2(s * scale - M) for this thread's 32 columns of half h, written as packed 16-bit pairs over the first
-    // half of the columns just read (the A operand of the PV product); returns the row-sum contribution
-    auto exp_half = [&](int h, int nv, float M) -> float {
-      if (nv <= 0) return 0.f;   // none of this thread's columns exist: the tensor core stops before them
-      uint32_t v[32], pk[16];
-      tmem_ld_x32(s_col + h * kHalfKV, v);
-      tmem_wait_ld();
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      if (nv == 32) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float e0 = fast_exp2(fmaf(__uint_as_float(v[j]), sl2, -M));
-          const float e1 = fast_exp2(fmaf(__uint_as_float(v[j + 1]), sl2, -M));
-          const float e2 = fast_exp2(fmaf(__uint_as_float(v[j + 2]), sl2, -M));
-          const float e3 = fast_exp2(fmaf(__uint_as_float(v[j + 3]), sl2, -M));
-          s0 += e0;
-          s1 += e1;
-          s2 += e2;
-          s3 += e3;
-          pk[j >> 1] = pack2<kBf16>(e0, e1);
-          pk[(j >> 1) + 1] = pack2<kBf16>(e2, e3);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float e0 = fast_exp2(fmaf(__uint_as_float(v[j]), sl2, -M));
-          float e1 = fast_exp2(fmaf(__uint_as_float(v[j + 1]), sl2, -M));
-          if (j >= nv) e0 = 0.f;      // select, not multiply: stale columns may hold NaN
-          if (j + 1 >= nv) e1 = 0.f;
-          s0 += e0;
-          s1 += e1;
-          pk[j >> 1] = pack2<kBf16>(e0, e1);
-        }
-      }
-      tmem_st_x16(s_col + h * kHalfKV, pk);
-      return (s0 + s1) + (s2 + s3);
-    };
+#ifdef DS_TRACE
+    int _tr_n = 0;
+    const int _tr_slot = warp == kWarpSoftmax0 ? 2 : 3;
+    const bool _tr_on = p.trace && blockIdx.x == 0 && lane == 0 && (warp == kWarpSoftmax0 || warp == 25);
+#endif
 
     for_each_group(p, [&](const GroupInfo& G) {
-      const int nvA = max(0, min(G.rowsA - qtr * 32, 32)), nvB = max(0, min(G.rowsB - qtr * 32, 32));
       const int n_half = G.rowsB ? 2 : 1;
-      // ---- pass 1: row maximum over the whole group
-      float m = -INFINITY;
 #pragma unroll 1
-      for (int h = 0; h < n_half; ++h) {
+      for (int h = 0; h < n_half; ++h, ++w) {
+        const int nv = max(0, min((h ? G.rowsB : G.rowsA) - qtr * 32, 32));   // valid columns of this thread's 32
+        const bool first = G.first_of_item && h == 0;
+        const bool last = G.last_of_item && h == n_half - 1;
+        DS_TRACE_EV(30 + h);
         mbar_wait(&s_full[h], (h ? cntB : cntA) & 1);
+        DS_TRACE_EV(32 + h);
         tc_fence_after_sync();
-        m = row_max(h, h ? nvB : nvA, m);
-      }
-      m *= sl2;
-      float* mx = sMax + (u & 1) * 512;
-      mx[qtr * 128 + row] = m;
-      named_bar_sync(1, 512);
-      float M = fmaxf(fmaxf(mx[row], mx[128 + row]), fmaxf(mx[256 + row], mx[384 + row]));
-      if (G.first_of_item) {
-        l_run = 0.f;
-      } else {
-        // online softmax across groups: publish the factor the epilogue warps rescale O with
-        M = fmaxf(m_run, M);
-        const float alpha = fast_exp2(m_run - M);
-        l_run *= alpha;
-        if (qtr == 0) {
-          tmem_st_x1(tmem_base + lane_addr + kTmemAlpha + (corr & 1), __float_as_uint(alpha));
-          tmem_wait_st();
-          tc_fence_before_sync();
-          mbar_arrive(alpha_full);
+        uint32_t v[32];
+        tmem_ld_x32(s_col + h * kHalfKV, v);   // also when nv == 0: stale columns, never used
+        tmem_wait_ld();
+        // ---- row maximum of this half (4 threads per row exchange through shared memory)
+        float m;
+        if (nv == 32) {
+          float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            a0 = fmaxf(a0, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+            a1 = fmaxf(a1, fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+            a2 = fmaxf(a2, fmaxf(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])));
+            a3 = fmaxf(a3, fmaxf(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])));
+          }
+          m = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+        } else {
+          m = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nv) m = fmaxf(m, __uint_as_float(v[j]));
         }
-        ++corr;
-      }
-      m_run = M;
-      // ---- pass 2 (in place: S_h -> P_h), half A then half B
+        m *= sl2;
+        float* mx = sMax + (w & 1) * 512;
+        mx[qtr * 128 + row] = m;
+        DS_TRACE_EV(34 + h);
+        named_bar_sync(1, 512);
+        DS_TRACE_EV(36 + h);
+        const float Mh = fmaxf(fmaxf(mx[row], mx[128 + row]), fmaxf(mx[256 + row], mx[384 + row]));
+        // lazy running maximum: p may grow up to 2^tau before the reference moves (fp16 P holds 2^14, bf16 anything)
+        constexpr float kTau = kBf16 ? 30.0f : 14.0f;
+        float alpha = 1.0f;
+        if (first) {
+          m_run = Mh;
+          l_run = 0.f;
+        } else if (Mh > m_run + kTau) {
+          // rare (the four threads of the row decide identically): move the reference, rescale the running sum
+          alpha = fast_exp2(m_run - Mh);
+          m_run = Mh;
+          l_run *= alpha;
+        }
+        if (qtr == 0 && !first) {
+          // ... and O, which the first-quarter thread of the row does before P is released
+          if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+            mbar_wait(pv_half, (w - 1) & 1);   // the previous half's PV has landed in O (phases <= w-2 are known complete)
+            tc_fence_after_sync();
+            {
 #pragma unroll 1
-      for (int h = 0; h < n_half; ++h) {
-        l_run += exp_half(h, h ? nvB : nvA, M);
-        if (G.last_of_item && h == n_half - 1)
-          tmem_st_x1(tmem_base + lane_addr + kTmemSum + 4 * (n & 1) + qtr, __float_as_uint(l_run));
+              for (int c = 0; c < C::D_PAD / 16; ++c) {
+                uint32_t o[16];
+                tmem_ld_x16(o_col + c * 16, o);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+                tmem_st_x16(o_col + c * 16, o);
+              }
+            }
+          }
+        }
+        // ---- p = exp2(s * scale - m_run), written as packed 16-bit pairs over the first half of the columns just
+        //      read (the A operand of the PV product)
+        if (nv > 0) {
+          uint32_t pk[16];
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          if (nv == 32) {
+            // packed fp32 pairs: one FFMA2 scales and shifts two logits, one FADD2 adds two terms to the row sum
+            const uint64_t sl2_2 = f2_pack(sl2, sl2), nm_2 = f2_pack(-m_run, -m_run);
+            uint64_t sum_a = 0ull, sum_b = 0ull;   // (+0.f, +0.f)
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float x0, x1, x2, x3;
+              f2_unpack(f2_fma(f2_pack_u(v[j], v[j + 1]), sl2_2, nm_2), x0, x1);
+              f2_unpack(f2_fma(f2_pack_u(v[j + 2], v[j + 3]), sl2_2, nm_2), x2, x3);
+              const float e0 = fast_exp2(x0), e1 = fast_exp2(x1), e2 = fast_exp2(x2), e3 = fast_exp2(x3);
+              sum_a = f2_add(sum_a, f2_pack(e0, e1));
+              sum_b = f2_add(sum_b, f2_pack(e2, e3));
+              pk[j >> 1] = pack2<kBf16>(e0, e1);
+              pk[(j >> 1) + 1] = pack2<kBf16>(e2, e3);
+            }
+            f2_unpack(f2_add(sum_a, sum_b), s0, s1);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              float e0 = fast_exp2(fmaf(__uint_as_float(v[j]), sl2, -m_run));
+              float e1 = fast_exp2(fmaf(__uint_as_float(v[j + 1]), sl2, -m_run));
+              if (j >= nv) e0 = 0.f;      // select, not multiply: stale columns may hold NaN
+              if (j + 1 >= nv) e1 = 0.f;
+              s0 += e0;
+              s1 += e1;
+              pk[j >> 1] = pack2<kBf16>(e0, e1);
+            }
+          }
+          tmem_st_x16(s_col + h * kHalfKV, pk);
+          l_run += (s0 + s1) + (s2 + s3);
+        }
+        if (last) tmem_st_x1(tmem_base + lane_addr + kTmemSum + 4 * (n & 1) + qtr, __float_as_uint(l_run));
         tmem_wait_st();
         tc_fence_before_sync();
         mbar_arrive(&p_full[h]);
+        DS_TRACE_EV(38 + h);
         if (h) ++cntB; else ++cntA;
+        if (last) ++n;
       }
-      if (G.last_of_item) ++n;
-      ++u;
     });
   } else {
-    // ------------------------------------------------------------------ epilogue / correction (warps 2-5)
+    // ------------------------------------------------------------------ epilogue (warps 2-9)
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    const uint32_t o_col = tmem_base + lane_addr + kTmemO;
-    const uint32_t os_col = tmem_base + lane_addr + kTmemOs;
+    const int dh = (warp - 2) >> 2;                       // which half of the 16-column chunks of O
+    constexpr int NC_ALL = C::D_PAD / 16;
+    constexpr int NC0 = (NC_ALL + 1) / 2;                 // chunks of the first half (the second gets the rest)
+    const int c_base = dh ? NC0 : 0;
+    const uint32_t o_col = tmem_base + lane_addr + kTmemO + c_base * 16;
+    const uint32_t os_col = tmem_base + lane_addr + kTmemOs + c_base * 8;
     const int tiles = p.B * p.H * p.n_qt;
-    uint32_t n = 0, corr = 0, ug = 0;   // items, corrections, kv groups seen
+    uint32_t n = 0;   // items seen
+#ifdef DS_TRACE
+    int _tr_n = 0;
+    const int _tr_slot = 4;
+    const bool _tr_on = p.trace && blockIdx.x == 0 && lane == 0 && warp == 2;
+#endif
     float ns_tile = 0.f;  // |O_self|^2 of the current stream (meaningful on the reducing thread)
     for_each_group(p, [&](const GroupInfo& G) {
-      if (!G.first_of_item) {
-        // rescale O by the factors of this group once the previous group's PV has landed (the previous group of an
-        // item is always complete, so its last product is PV_B)
-        mbar_wait(alpha_full, corr & 1);
-        mbar_wait(o_full, (ug - 1) & 1);
-        tc_fence_after_sync();
-        const float alpha = __uint_as_float(tmem_ld_x1(tmem_base + lane_addr + kTmemAlpha + (corr & 1)));
-        tmem_wait_ld();
-        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
-#pragma unroll 1
-          for (int c = 0; c < C::D_PAD / 16; ++c) {
-            uint32_t v[16];
-            tmem_ld_x16(o_col + c * 16, v);
-            tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
-            tmem_st_x16(o_col + c * 16, v);
-          }
-          tmem_wait_st();
-        }
-        tc_fence_before_sync();
-        mbar_arrive(corr_done);
-        ++corr;
-      }
-      const uint32_t gpar = ug & 1;
-      ++ug;
       if (!G.last_of_item) return;
-
       const uint32_t par = n & 1;
+      // one phase per item; the tensor core cannot complete the next item before this warp has released O
+      mbar_wait(o_full, par);
+      DS_TRACE_EV(40);
+
       const bool row_ok = G.qt * kBlockQ + row < p.Sq;
-      mbar_wait(o_full, gpar);
       tc_fence_after_sync();
       float inv_l;
       {
@@ -505,18 +531,29 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         tmem_wait_ld();
         inv_l = 1.0f / ((__uint_as_float(s0) + __uint_as_float(s1)) + (__uint_as_float(s2) + __uint_as_float(s3)));
       }
-      float acc0 = 0.f, acc1 = 0.f;   // cosine: dot / |Oc|^2 (cross), |Os|^2 (self); mse: sum of squared differences
+      // cosine: (acc0+acc1) = dot (cross) or |Os|^2 (self), (acc2+acc3) = |Oc|^2; mse: (acc0+acc1) = sum of squared differences
+      uint64_t acc01 = 0ull, acc23 = 0ull;   // packed fp32 pairs, (+0.f, +0.f)
       uint8_t* out_row = nullptr;
       if constexpr (MODE == ATTN_MODE_STORE)
         out_row = static_cast<uint8_t*>(p.out) + 2 * ((int64_t)G.b * p.out_sb + (int64_t)G.h * p.out_sh +
-                                                     (int64_t)(G.qt * kBlockQ + row) * p.out_ss);
-#pragma unroll 1
-      for (int c = 0; c < C::D_PAD / 16; ++c) {
-        uint32_t v[16];
-        tmem_ld_x16(o_col + c * 16, v);
-        tmem_wait_ld();
-        if (c == C::D_PAD / 16 - 1) {
-          // O is in registers: the MMA warp may start the next item's PV
+                                                     (int64_t)(G.qt * kBlockQ + row) * p.out_ss + c_base * 16);
+      const bool cross = (MODE != ATTN_MODE_STORE) && !G.self;
+      constexpr int NC = NC0;                 // trip count of the unrolled loop; the second half may own one chunk less
+      const int nc_mine = dh ? NC_ALL - NC0 : NC0;
+      // software pipeline over the 16-column chunks of O: the TMEM loads of chunk c+1 are in flight while chunk c is
+      // consumed; O is released to the tensor core as soon as its last chunk has landed in registers
+      uint32_t v[2][16], os[2][8];
+      tmem_ld_x16(o_col, v[0]);
+      if (cross) tmem_ld_x8(os_col, os[0]);
+      tmem_wait_ld();
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const int cur = c & 1;
+        if (c >= nc_mine) break;
+        if (c + 1 < nc_mine) {
+          tmem_ld_x16(o_col + (c + 1) * 16, v[cur ^ 1]);
+          if (cross) tmem_ld_x8(os_col + (c + 1) * 8, os[cur ^ 1]);
+        } else {
           tc_fence_before_sync();
           mbar_arrive(o_empty);
         }
@@ -524,85 +561,78 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           uint32_t pk[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            pk[j] = pack2<kBf16>(__uint_as_float(v[2 * j]) * inv_l, __uint_as_float(v[2 * j + 1]) * inv_l);
+            pk[j] = pack2<kBf16>(__uint_as_float(v[cur][2 * j]) * inv_l, __uint_as_float(v[cur][2 * j + 1]) * inv_l);
           if (row_ok) {
 #pragma unroll
             for (int hlf = 0; hlf < 2; ++hlf) {
-              if (c * 16 + hlf * 8 < D) {
-                uint4 w = make_uint4(pk[4 * hlf], pk[4 * hlf + 1], pk[4 * hlf + 2], pk[4 * hlf + 3]);
-                *reinterpret_cast<uint4*>(out_row + (c * 16 + hlf * 8) * 2) = w;
+              if ((c_base + c) * 16 + hlf * 8 < D) {
+                uint4 w4 = make_uint4(pk[4 * hlf], pk[4 * hlf + 1], pk[4 * hlf + 2], pk[4 * hlf + 3]);
+                *reinterpret_cast<uint4*>(out_row + (c * 16 + hlf * 8) * 2) = w4;
               }
             }
           }
-        } else if (G.self) {
+        } else if (!cross) {
           // O_self is rounded to the input dtype (as the reference's SDPA output is) and kept in TMEM
           uint32_t pk[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            pk[j] = pack2<kBf16>(__uint_as_float(v[2 * j]) * inv_l, __uint_as_float(v[2 * j + 1]) * inv_l);
+            pk[j] = pack2<kBf16>(__uint_as_float(v[cur][2 * j]) * inv_l, __uint_as_float(v[cur][2 * j + 1]) * inv_l);
           tmem_st_x8(os_col + c * 8, pk);
           if constexpr (MODE == ATTN_MODE_COS) {
             // |O_self|^2 from the unrounded values, normalised once per row below (differs from the norm of the
             // rounded vector by O(eps^2))
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
-              acc0 = fmaf(__uint_as_float(v[j]), __uint_as_float(v[j]), acc0);
-              acc1 = fmaf(__uint_as_float(v[j + 1]), __uint_as_float(v[j + 1]), acc1);
+              const uint64_t o2 = f2_pack_u(v[cur][j], v[cur][j + 1]);
+              acc01 = f2_fma(o2, o2, acc01);
             }
+          }
+        } else if constexpr (MODE == ATTN_MODE_COS) {
+          // unnormalised: dot = inv_l * sum o s, |Oc|^2 = inv_l^2 * sum o^2 (applied once per row below)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 sv = unpack2<kBf16>(os[cur][j]);
+            const uint64_t o2 = f2_pack_u(v[cur][2 * j], v[cur][2 * j + 1]);
+            acc01 = f2_fma(o2, f2_pack(sv.x, sv.y), acc01);
+            acc23 = f2_fma(o2, o2, acc23);
           }
         } else {
-          uint32_t os[8];
-          tmem_ld_x8(os_col + c * 8, os);
-          tmem_wait_ld();
-          if constexpr (MODE == ATTN_MODE_COS) {
-            // unnormalised: dot = inv_l * sum o s, |Oc|^2 = inv_l^2 * sum o^2 (applied once per row below)
+          const uint64_t inv_l2 = f2_pack(inv_l, inv_l);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float2 s = unpack2<kBf16>(os[j]);
-              const float ox = __uint_as_float(v[2 * j]), oy = __uint_as_float(v[2 * j + 1]);
-              acc0 = fmaf(ox, s.x, acc0);
-              acc0 = fmaf(oy, s.y, acc0);
-              acc1 = fmaf(ox, ox, acc1);
-              acc1 = fmaf(oy, oy, acc1);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float2 s = unpack2<kBf16>(os[j]);
-              const float dx = fmaf(__uint_as_float(v[2 * j]), inv_l, -s.x);
-              const float dy = fmaf(__uint_as_float(v[2 * j + 1]), inv_l, -s.y);
-              acc0 = fmaf(dx, dx, acc0);
-              acc1 = fmaf(dy, dy, acc1);
-            }
+          for (int j = 0; j < 8; ++j) {
+            const float2 sv = unpack2<kBf16>(os[cur][j]);
+            const uint64_t d2 = f2_fma(f2_pack_u(v[cur][2 * j], v[cur][2 * j + 1]), inv_l2, f2_pack(-sv.x, -sv.y));
+            acc01 = f2_fma(d2, d2, acc01);
           }
         }
+        if (c + 1 < nc_mine) tmem_wait_ld();
       }
       if constexpr (MODE != ATTN_MODE_STORE) {
         if (G.self) tmem_wait_st();
         float r0, r1;   // cross: (dot, |Oc|^2) or (sq, 0); self: (|Os|^2, 0)
         if (G.self) {
-          r0 = (acc0 + acc1) * inv_l * inv_l;
+          r0 = f2_hsum(acc01) * inv_l * inv_l;
           r1 = 0.f;
         } else if constexpr (MODE == ATTN_MODE_COS) {
-          r0 = acc0 * inv_l;
-          r1 = acc1 * inv_l * inv_l;
+          r0 = f2_hsum(acc01) * inv_l;
+          r1 = f2_hsum(acc23) * inv_l * inv_l;
         } else {
-          r0 = acc0 + acc1;
+          r0 = f2_hsum(acc01);
           r1 = 0.f;
         }
         if (!row_ok) r0 = r1 = 0.f;
         // fixed-order reduction over the 128 rows: shuffle tree, then warps 0..3 in order
         r0 = warp_sum(r0);
         r1 = warp_sum(r1);
-        float* red = sRed + par * 16;
+        float* red = sRed + par * 16;   // [8 warps][2]
         if (lane == 0) {
-          red[quad * 4 + 0] = r0;
-          red[quad * 4 + 1] = r1;
+          red[(dh * 4 + quad) * 2 + 0] = r0;
+          red[(dh * 4 + quad) * 2 + 1] = r1;
         }
-        named_bar_sync(2, 128);
-        if (quad == 0 && lane == 0) {
-          const float t0 = (red[0] + red[4]) + (red[8] + red[12]);
-          const float t1 = (red[1] + red[5]) + (red[9] + red[13]);
+        named_bar_sync(2, 256);
+        if (warp == 2 && lane == 0) {
+          const float t0 = ((red[0] + red[2]) + (red[4] + red[6])) + ((red[8] + red[10]) + (red[12] + red[14]));
+          const float t1 = ((red[1] + red[3]) + (red[5] + red[7])) + ((red[9] + red[11]) + (red[13] + red[15]));
           if (G.self) {
             ns_tile = t0;
           } else if constexpr (MODE == ATTN_MODE_COS) {
@@ -612,12 +642,14 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           }
         }
       }
+      DS_TRACE_EV(41);
       ++n;
     });
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == kWarpMma) tmem_dealloc(tmem_base, kTmemCols);
+  if (p.cycles && blockIdx.x == 0 && threadIdx.x == 0) *p.cycles = (unsigned long long)(clock64() - clk_start);
 }
 
 // dir[t] from the per-tile partials, tiles added in index order (deterministic)
@@ -783,6 +815,9 @@ static int make_map(CUtensorMap* m, const ds_tensor5& t, int subw, int rows) {
   return encode_tensor_map(m, t.dtype, 5, t.ptr, dims, strides, box, subw * 2);
 }
 
+static unsigned long long* g_trace_ptr = nullptr;
+static int g_trace_cap = 0;
+
 struct AttnLaunch {
   ds_tensor5 q, ks, vs, k, v;
   AttnParams p;
@@ -820,6 +855,9 @@ static int launch_attn_d(const AttnLaunch& a, cudaStream_t st) {
   if ((rc = make_map(&mk, a.k, C::SUBW, kHalfKV)) != DS_OK) return rc;
   if ((rc = make_map(&mv, a.v, C::SUBW, kHalfKV)) != DS_OK) return rc;
   const int64_t n_streams = (int64_t)a.p.n_groups * a.p.B * a.p.H * a.p.n_qt;
+  const_cast<AttnLaunch&>(a).p.trace = g_trace_ptr;
+  const_cast<AttnLaunch&>(a).p.trace_cap = g_trace_cap;
+  const_cast<AttnLaunch&>(a).p.cycles = g_trace_ptr ? g_trace_ptr + (size_t)8 * g_trace_cap : nullptr;
   int grid = sm_count();
   if (n_streams < grid) grid = (int)n_streams;
   if (grid <= 0) return DS_OK;
@@ -895,6 +933,16 @@ static ds_tensor5 lift(const ds_tensor4& t) {
 }  // namespace ds
 
 extern "C" {
+
+int ds_debug_set_trace(void* dev_buf, int cap) {
+  ds::g_trace_ptr = static_cast<unsigned long long*>(dev_buf);
+  ds::g_trace_cap = cap;
+#ifdef DS_TRACE
+  return 1;
+#else
+  return 0;
+#endif
+}
 
 size_t ds_attn_fwd_workspace_bytes(ds_tensor4 q, ds_tensor4 k) {
   (void)q;

@@ -83,6 +83,13 @@ int         ds_device_ok(void);
 int ds_profile_enable(int on);
 int ds_profile_collect(float* total_ms, int* launches);
 
+/*
+ * Debug only: device buffer of 8 x cap + 1 64-bit words.  A library built with -DDS_TRACE fills the first
+ * 8 x cap words with (tag << 48 | SM clock) events of CTA 0 of the attention kernel; every build stores the SM
+ * clocks CTA 0 spent in the last attention launch in word [8 x cap].  Returns 1 if tracing is compiled in, else 0.
+ */
+int ds_debug_set_trace(void* dev_buf, int cap);
+
 /* ---- K1: attention ------------------------------------------------------ */
 
 /*

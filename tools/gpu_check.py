@@ -115,6 +115,9 @@ def _attn_inputs(B, H, Sq, Skv, D, dtype, seed=0, kind="random"):
         return mem.to(dtype).cuda().view(B, S, H, D).transpose(1, 2)
 
     q, k, v = mk(Sq, 1.5), mk(Skv, 1.5), mk(Skv, 1.0)
+    if kind == "ramp":     # later kv rows carry much larger logits: forces the lazy running maximum to move (O rescale path)
+        ramp = (1.0 + 9.0 * torch.arange(Skv).float() / Skv).view(1, 1, Skv, 1).cuda()
+        k = (k.float() * ramp).to(dtype)
     if kind == "pv":       # K = 0: uniform softmax, O = mean(V): isolates the P-write + PV (V descriptor) path
         k = torch.zeros_like(k)
     elif kind == "qk":     # V = one-hot over d: O[:, d] = sum_{j = d mod D} P[:, j]: exposes P (hence S = QK^T)
@@ -234,6 +237,10 @@ def case_attn_long():
     ok &= _attn_case(1, 2, 512, 4096, 40, torch.float16)     # SD-1.5 up_blocks[2]-like
     ok &= _attn_case(1, 2, 4096, 4096, 64, torch.bfloat16)   # SDXL up_blocks[1]-like
     ok &= _attn_case(1, 1, 300, 700, 160, torch.float16)
+    ok &= _attn_case(1, 2, 256, 256, 64, torch.float16, "ramp")
+    ok &= _attn_case(1, 2, 256, 1024, 64, torch.float16, "ramp")
+    ok &= _attn_case(1, 2, 256, 256, 160, torch.float16, "ramp")
+    ok &= _attn_case(1, 2, 128, 2048, 64, torch.bfloat16, "ramp")
     return ok
 
 
@@ -344,6 +351,14 @@ def case_perf():
                          dtype=torch.int32, device=dev)
     ms = timeit(lambda: ops.aas_pairs(q, k, v, pairs, "cosine"), iters=10)
     P = pairs.shape[0]
+    from diffsim_b200 import _native as N
+    cyc = torch.zeros(8 * 4 + 1, dtype=torch.int64, device=dev)
+    N.load().ds_debug_set_trace(cyc.data_ptr(), 4)
+    ops.aas_pairs(q, k, v, pairs, "cosine")
+    torch.cuda.synchronize()
+    N.load().ds_debug_set_trace(None, 0)
+    items_per_sm = 4 * P * B * H * (S // 128) / 148
+    print(f"[perf aas_pairs cycles] CTA0 {int(cyc[-1])} SM clocks, {int(cyc[-1]) / items_per_sm:.0f} clk per item (tensor floor 2560)")
     fl = 4 * P * 4 * B * H * S * S * D
     print(f"[perf aas_pairs sd15_up0 fp16] {P} pairs {ms:.3f} ms  {P / ms * 1e3:.0f} pairs/s  {fl / ms / 1e9:.1f} TFLOP/s")
     res["aas_pairs_tflops"] = fl / ms / 1e9
