@@ -597,11 +597,16 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             acc23 = f2_fma(o2, o2, acc23);
           }
         } else {
+          // MSE: the cross output is rounded to the input dtype like O_self (and like the reference's SDPA outputs), so
+          // that an image scored against itself gives exactly 0
           const uint64_t inv_l2 = f2_pack(inv_l, inv_l);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float2 sv = unpack2<kBf16>(os[cur][j]);
-            const uint64_t d2 = f2_fma(f2_pack_u(v[cur][2 * j], v[cur][2 * j + 1]), inv_l2, f2_pack(-sv.x, -sv.y));
+            float x0, x1;
+            f2_unpack(f2_mul(f2_pack_u(v[cur][2 * j], v[cur][2 * j + 1]), inv_l2), x0, x1);
+            const float2 ov = unpack2<kBf16>(pack2<kBf16>(x0, x1));
+            const uint64_t d2 = f2_add(f2_pack(ov.x, ov.y), f2_pack(-sv.x, -sv.y));
             acc01 = f2_fma(d2, d2, acc01);
           }
         }

@@ -77,6 +77,45 @@ def test_attn_fwd_explicit_scale_and_dit_layout():
     assert (out.double().cpu() - O.attention(q, k, v, scale=0.05)).abs().max().item() < 4e-3
 
 
+# kv lengths beyond one 256-row group (SDXL up_blocks 1024 / 4096 tokens, SD-1.5 up_blocks[1..2]): the online
+# softmax with the lazy running maximum; "ramp" inputs make later kv rows dominate so that the rescale path runs.
+@pytest.mark.parametrize("case", [(1, 2, 128, 320, 64, torch.float16, "random"), (1, 2, 200, 448, 64, torch.float16, "random"),
+                                  (2, 4, 1024, 1024, 64, torch.float16, "random"), (1, 2, 1024, 1024, 80, torch.float16, "random"),
+                                  (1, 2, 512, 4096, 40, torch.float16, "random"), (1, 2, 4096, 4096, 64, torch.bfloat16, "random"),
+                                  (1, 1, 300, 700, 160, torch.float16, "random"), (1, 2, 256, 256, 160, torch.float16, "ramp"),
+                                  (1, 2, 256, 1024, 64, torch.float16, "ramp"), (1, 2, 128, 2048, 64, torch.bfloat16, "ramp")])
+def test_attn_fwd_long_kv_and_rescale_path(case):
+    dev = _cuda()
+    from diffsim_b200 import ops
+
+    B, H, Sq, Skv, D, dtype, kind = case
+    q, k, v = _rand_qkv(B, H, Sq, Skv, D, dtype, Skv + D, dev)
+    if kind == "ramp":
+        ramp = (1.0 + 9.0 * torch.arange(Skv, device=k.device).float() / Skv).view(1, 1, Skv, 1)
+        k = (k.float() * ramp).to(dtype)
+    out = ops.attn_fwd(q, k, v)
+    ref = O.attention(q.cpu(), k.cpu(), v.cpu())
+    tol = 2e-2 if dtype == torch.bfloat16 else 4e-3
+    err = (out.double().cpu() - ref).abs().max().item()
+    assert torch.isfinite(out).all() and err <= tol * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("shape,dtype", [((2, 4, 640, 64), torch.float16), ((1, 2, 1024, 64), torch.bfloat16),
+                                         ((2, 10, 1024, 64), torch.float16)])
+def test_aas_pairs_long_kv(shape, dtype):
+    """AAS pair scores at SDXL-like token counts (diffsim/diffsim_xl.py:135-155) against the T1 oracle."""
+    dev = _cuda()
+    from diffsim_b200 import ops, synth
+
+    m = synth.SynthModel(*shape, seed=2334)
+    images, pairs = synth.make_pairs(m, 2, dtype, seed=9)
+    q, k, v = synth.stack_cache(images, dev)
+    for sim in ("cosine", "mse"):
+        got = ops.aas_pairs(q, k, v, pairs, sim).cpu().double()
+        ref = torch.tensor([O.aas_pair_score(*images[a], *images[b], mode=sim) for a, b in pairs], dtype=torch.float64)
+        assert ((got - ref).abs() / ref.abs().clamp_min(1e-9)).max().item() < REL_16BIT
+
+
 def test_unsupported_requests_fail_loudly():
     dev = _cuda()
     from diffsim_b200 import ops
