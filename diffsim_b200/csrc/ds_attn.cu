@@ -60,7 +60,7 @@ constexpr int kTmemS = 0;        // S_A: columns [0,128), S_B: [128,256); P of t
                                  // overwrites the first 16 of its own 32 S columns
 constexpr int kTmemO = 256;      // O: [256, 256 + D_PAD)
 constexpr int kTmemOs = 416;     // O_self, packed 16-bit: [416, 416 + D_PAD/2)
-constexpr int kTmemSum = 496;    // row sums: 496 + 4 * (item parity) + (column quarter of the thread)
+constexpr int kTmemL = 496;      // softmax denominators l = P . 1 (a 16-column MMA against a constant ones tile): [496,512)
 
 template <int D>
 struct AttnCfg {
@@ -74,13 +74,13 @@ struct AttnCfg {
   static constexpr int Q_BYTES = NSUB * Q_SUB_BYTES;
   static constexpr int KV_SUB_BYTES = kHalfKV * SUB_BYTES;
   static constexpr int STAGE_BYTES = NSUB * KV_SUB_BYTES;
-  static constexpr int MISC_BYTES = 4096 /*max exchange*/ + 128 /*epilogue reduce*/ + 512 /*barriers*/;
+  static constexpr int MISC_BYTES = 2048 /*ones tile*/ + 4096 /*max exchange*/ + 128 /*epilogue reduce*/ + 512 /*barriers*/;
   static constexpr int kMaxSmem = 232448;
   static constexpr int STAGES_RAW = (kMaxSmem - Q_BYTES - MISC_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 12 ? 12 : STAGES_RAW;
   static constexpr int SMEM_BYTES = Q_BYTES + STAGES * STAGE_BYTES + MISC_BYTES;
   static_assert(STAGES >= 4, "not enough shared memory for the K/V ring");
-  static_assert(kTmemO + D_PAD <= kTmemOs && kTmemOs + D_PAD / 2 <= kTmemSum, "TMEM budget");
+  static_assert(kTmemO + D_PAD <= kTmemOs && kTmemOs + D_PAD / 2 <= kTmemL, "TMEM budget");
   static_assert(Q_BYTES % 1024 == 0 && STAGE_BYTES % 1024 == 0, "swizzle atoms need 1024-byte aligned tiles");
 };
 
@@ -127,24 +127,34 @@ struct GroupInfo {
 
 template <typename F>
 __device__ __forceinline__ void for_each_group(const AttnParams& p, F&& f) {
-  const int BH = p.B * p.H;
-  const int64_t n_streams = (int64_t)p.n_groups * BH * p.n_qt;
+  const uint32_t BH = (uint32_t)(p.B * p.H);
+  const uint32_t n_streams = (uint32_t)p.n_groups * BH * (uint32_t)p.n_qt;   // < 2^31, checked by the host
   const int n_grp = (p.Skv + kGroupKV - 1) / kGroupKV;
-  // stream -> (bh, group, q tile): q tile fastest so that neighbouring CTAs share K/V in L2
-  for (int64_t st = blockIdx.x; st < n_streams; st += gridDim.x) {
+  // stream -> (bh, group, q tile): q tile fastest so that neighbouring CTAs share K/V in L2.  32-bit arithmetic only:
+  // this decode sits between two items on every role's critical path.
+  for (uint32_t st = blockIdx.x; st < n_streams; st += gridDim.x) {
     GroupInfo G;
-    G.qt = (int)(st % p.n_qt);
-    const int64_t r = st / p.n_qt;
-    const int g = (int)(r % p.n_groups);
-    G.bh = (int)(r / p.n_groups);
+    const uint32_t r = st / (uint32_t)p.n_qt;
+    G.qt = (int)(st - r * (uint32_t)p.n_qt);
+    G.bh = (int)(r / (uint32_t)p.n_groups);
+    const int g = (int)(r - (uint32_t)G.bh * (uint32_t)p.n_groups);
     G.b = G.bh / p.H;
-    G.h = G.bh % p.H;
+    G.h = G.bh - G.b * p.H;
+    // the work list lives in global memory and every role walks it between barriers the compiler cannot move loads
+    // across: pull the entries of the NEXT stream / item into L1 now so that the dependent loads below hit
+    if (st + gridDim.x < n_streams) {
+      const uint32_t r_n = (st + gridDim.x) / (uint32_t)p.n_qt;
+      const uint32_t g_n = r_n % (uint32_t)p.n_groups;
+      prefetch_l1(p.group_q + g_n);
+      prefetch_l1(p.group_off + g_n);
+    }
     G.qi = p.group_q[g];
     const int t0 = p.group_off[g], t1 = p.group_off[g + 1];
     const int n_items = (t1 - t0) + p.self_first;
     for (int it = 0; it < n_items; ++it) {
       G.self = p.self_first && it == 0;
       G.entry = t0 + it - p.self_first;
+      if (it + 1 < n_items) prefetch_l1(p.kv_idx + G.entry + 1);
       G.img = G.self ? G.qi : p.kv_idx[G.entry];
       for (int gg = 0; gg < n_grp; ++gg) {
         G.kv0 = gg * kGroupKV;
@@ -170,7 +180,8 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sRing = sQ + C::Q_BYTES;
-  float* sMax = reinterpret_cast<float*>(sRing + C::STAGES * C::STAGE_BYTES);  // [2 parity][4 col quarter][128]
+  uint8_t* sOnes = sRing + C::STAGES * C::STAGE_BYTES;   // [16 rows][64] K-major tile: row 0 = 1.0, rows 1..15 = 0
+  float* sMax = reinterpret_cast<float*>(sOnes + 2048);  // [2 parity][4 col quarter][128]
   float* sRed = sMax + 1024;                                                   // [2 parity][4 warps][4]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 32);
   uint64_t* q_full = bars + 0;
@@ -219,6 +230,13 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
+  // constant B operand of the row-sum MMA: l[r] = sum_k P[r,k] * 1.  Row 0 of a 128B-swizzled K-major tile is not
+  // permuted (its swizzle XOR is 0) and the other rows are all zero, so the fill is layout-trivial.
+  if (threadIdx.x < 512) {
+    const uint32_t one2 = kBf16 ? 0x3F803F80u : 0x3C003C00u;
+    reinterpret_cast<uint32_t*>(sOnes)[threadIdx.x] = threadIdx.x < 32 ? one2 : 0u;
+  }
+  fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -276,6 +294,8 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     if (elect_one()) {
       const uint32_t fmt = kBf16 ? 1u : 0u;
       const uint32_t idesc_pv = umma_idesc_f16(fmt, kBlockQ, C::D_PAD, 0, 1);
+      const uint32_t idesc_l = umma_idesc_f16(fmt, kBlockQ, 16, 0, 0);
+      const uint64_t ones_desc = umma_smem_desc(smem_u32(sOnes), 16, 1024, UMMA_SW128);
       constexpr uint32_t SBO = 8 * C::SUB_BYTES;  // eight swizzle rows
       // descriptors of the buffer bases; tiles are addressed by adding (byte offset >> 4) to the low word
       const uint64_t q_desc0 = umma_smem_desc(smem_u32(sQ), 16, SBO, C::LAYOUT);
@@ -336,6 +356,7 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           const uint32_t a_tmem = tmem_base + kTmemS + h * kHalfKV + (ks >> 1) * 32 + (ks & 1) * 8;
           const uint32_t acc = (G.first_of_item && h == 0 && ks == 0) ? 0u : 1u;
           umma_f16_ts(tmem_base + kTmemO, a_tmem, v_desc + (uint64_t)((ks * 16 * C::SUB_BYTES) >> 4), idesc_pv, acc);
+          umma_f16_ts(tmem_base + kTmemL, a_tmem, ones_desc, idesc_l, acc);   // l += P . 1
         }
         umma_commit(&kv_empty[stage]);
         advance();
@@ -371,8 +392,8 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const uint32_t s_col = tmem_base + lane_addr + kTmemS + qtr * 32;   // + h * 128; P goes to the first 16 of the 32
     const uint32_t o_col = tmem_base + lane_addr + kTmemO;
     const float sl2 = p.scale_log2;
-    uint32_t cntA = 0, cntB = 0, w = 0, n = 0;   // halves A / B seen, half-steps, items
-    float m_run = 0.f, l_run = 0.f;
+    uint32_t cntA = 0, cntB = 0, w = 0;   // halves A / B seen, half-steps
+    float m_run = 0.f;
 #ifdef DS_TRACE
     int _tr_n = 0;
     const int _tr_slot = warp == kWarpSoftmax0 ? 2 : 3;
@@ -385,7 +406,6 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       for (int h = 0; h < n_half; ++h, ++w) {
         const int nv = max(0, min((h ? G.rowsB : G.rowsA) - qtr * 32, 32));   // valid columns of this thread's 32
         const bool first = G.first_of_item && h == 0;
-        const bool last = G.last_of_item && h == n_half - 1;
         DS_TRACE_EV(30 + h);
         mbar_wait(&s_full[h], (h ? cntB : cntA) & 1);
         DS_TRACE_EV(32 + h);
@@ -415,82 +435,64 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         float* mx = sMax + (w & 1) * 512;
         mx[qtr * 128 + row] = m;
         DS_TRACE_EV(34 + h);
-        named_bar_sync(1, 512);
+        named_bar_sync(1 + quad, 128);   // the four warps of this TMEM quadrant (= of this scheduler) hold the row
         DS_TRACE_EV(36 + h);
         const float Mh = fmaxf(fmaxf(mx[row], mx[128 + row]), fmaxf(mx[256 + row], mx[384 + row]));
-        // lazy running maximum: p may grow up to 2^tau before the reference moves (fp16 P holds 2^14, bf16 anything)
+        // Lazy running maximum: the first half of the item fixes the row's reference m_run; a later half keeps it and
+        // simply lets p = exp2(s - m_run) grow -- up to 2^14 for fp16 P, 2^30 for bf16 -- which 16-bit P and the fp32
+        // accumulators hold without loss (the offset cancels in O / l).  Only beyond that does the reference move, which
+        // rescales O and l (rare; the four threads of the row decide identically).
         constexpr float kTau = kBf16 ? 30.0f : 14.0f;
         float alpha = 1.0f;
         if (first) {
           m_run = Mh;
-          l_run = 0.f;
         } else if (Mh > m_run + kTau) {
-          // rare (the four threads of the row decide identically): move the reference, rescale the running sum
           alpha = fast_exp2(m_run - Mh);
           m_run = Mh;
-          l_run *= alpha;
         }
         if (qtr == 0 && !first) {
-          // ... and O, which the first-quarter thread of the row does before P is released
+          // the first-quarter thread of a row rescales O and l before P is released
           if (__any_sync(0xffffffffu, alpha != 1.0f)) {
             mbar_wait(pv_half, (w - 1) & 1);   // the previous half's PV has landed in O (phases <= w-2 are known complete)
             tc_fence_after_sync();
-            {
 #pragma unroll 1
-              for (int c = 0; c < C::D_PAD / 16; ++c) {
-                uint32_t o[16];
-                tmem_ld_x16(o_col + c * 16, o);
-                tmem_wait_ld();
+            for (int c = 0; c < C::D_PAD / 16; ++c) {
+              uint32_t o[16];
+              tmem_ld_x16(o_col + c * 16, o);
+              tmem_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
-                tmem_st_x16(o_col + c * 16, o);
-              }
+              for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+              tmem_st_x16(o_col + c * 16, o);
             }
+            const uint32_t l_addr = tmem_base + lane_addr + kTmemL;
+            const float lv = __uint_as_float(tmem_ld_x1(l_addr));
+            tmem_wait_ld();
+            tmem_st_x1(l_addr, __float_as_uint(lv * alpha));
           }
         }
-        // ---- p = exp2(s * scale - m_run), written as packed 16-bit pairs over the first half of the columns just
-        //      read (the A operand of the PV product)
+        // ---- p = exp2(s * scale - m), written as packed 16-bit pairs over the first half of the columns just read (the A
+        //      operand of the PV product); the row sum is taken by the tensor core (ones column)
         if (nv > 0) {
           uint32_t pk[16];
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-          if (nv == 32) {
-            // packed fp32 pairs: one FFMA2 scales and shifts two logits, one FADD2 adds two terms to the row sum
-            const uint64_t sl2_2 = f2_pack(sl2, sl2), nm_2 = f2_pack(-m_run, -m_run);
-            uint64_t sum_a = 0ull, sum_b = 0ull;   // (+0.f, +0.f)
+          const uint64_t sl2_2 = f2_pack(sl2, sl2), nm_2 = f2_pack(-m_run, -m_run);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float x0, x1, x2, x3;
-              f2_unpack(f2_fma(f2_pack_u(v[j], v[j + 1]), sl2_2, nm_2), x0, x1);
-              f2_unpack(f2_fma(f2_pack_u(v[j + 2], v[j + 3]), sl2_2, nm_2), x2, x3);
-              const float e0 = fast_exp2(x0), e1 = fast_exp2(x1), e2 = fast_exp2(x2), e3 = fast_exp2(x3);
-              sum_a = f2_add(sum_a, f2_pack(e0, e1));
-              sum_b = f2_add(sum_b, f2_pack(e2, e3));
-              pk[j >> 1] = pack2<kBf16>(e0, e1);
-              pk[(j >> 1) + 1] = pack2<kBf16>(e2, e3);
-            }
-            f2_unpack(f2_add(sum_a, sum_b), s0, s1);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              float e0 = fast_exp2(fmaf(__uint_as_float(v[j]), sl2, -m_run));
-              float e1 = fast_exp2(fmaf(__uint_as_float(v[j + 1]), sl2, -m_run));
-              if (j >= nv) e0 = 0.f;      // select, not multiply: stale columns may hold NaN
+          for (int j = 0; j < 32; j += 2) {
+            float x0, x1;
+            f2_unpack(f2_fma(f2_pack_u(v[j], v[j + 1]), sl2_2, nm_2), x0, x1);
+            float e0 = fast_exp2(x0), e1 = fast_exp2(x1);
+            if (nv < 32) {             // select, not multiply: stale columns may hold NaN
+              if (j >= nv) e0 = 0.f;
               if (j + 1 >= nv) e1 = 0.f;
-              s0 += e0;
-              s1 += e1;
-              pk[j >> 1] = pack2<kBf16>(e0, e1);
             }
+            pk[j >> 1] = pack2<kBf16>(e0, e1);
           }
           tmem_st_x16(s_col + h * kHalfKV, pk);
-          l_run += (s0 + s1) + (s2 + s3);
         }
-        if (last) tmem_st_x1(tmem_base + lane_addr + kTmemSum + 4 * (n & 1) + qtr, __float_as_uint(l_run));
         tmem_wait_st();
         tc_fence_before_sync();
         mbar_arrive(&p_full[h]);
         DS_TRACE_EV(38 + h);
         if (h) ++cntB; else ++cntA;
-        if (last) ++n;
       }
     });
   } else {
@@ -523,13 +525,9 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       tc_fence_after_sync();
       float inv_l;
       {
-        uint32_t s0, s1, s2, s3;
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(s0), "=r"(s1), "=r"(s2), "=r"(s3)
-                     : "r"(tmem_base + lane_addr + kTmemSum + 4 * par)
-                     : "memory");
+        const uint32_t lv = tmem_ld_x1(tmem_base + lane_addr + kTmemL);
         tmem_wait_ld();
-        inv_l = 1.0f / ((__uint_as_float(s0) + __uint_as_float(s1)) + (__uint_as_float(s2) + __uint_as_float(s3)));
+        inv_l = 1.0f / __uint_as_float(lv);
       }
       // cosine: (acc0+acc1) = dot (cross) or |Os|^2 (self), (acc2+acc3) = |Oc|^2; mse: (acc0+acc1) = sum of squared differences
       uint64_t acc01 = 0ull, acc23 = 0ull;   // packed fp32 pairs, (+0.f, +0.f)
@@ -634,7 +632,7 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           red[(dh * 4 + quad) * 2 + 0] = r0;
           red[(dh * 4 + quad) * 2 + 1] = r1;
         }
-        named_bar_sync(2, 256);
+        named_bar_sync(5, 256);
         if (warp == 2 && lane == 0) {
           const float t0 = ((red[0] + red[2]) + (red[4] + red[6])) + ((red[8] + red[10]) + (red[12] + red[14]));
           const float t1 = ((red[1] + red[3]) + (red[5] + red[7])) + ((red[9] + red[11]) + (red[13] + red[15]));
@@ -860,6 +858,7 @@ static int launch_attn_d(const AttnLaunch& a, cudaStream_t st) {
   if ((rc = make_map(&mk, a.k, C::SUBW, kHalfKV)) != DS_OK) return rc;
   if ((rc = make_map(&mv, a.v, C::SUBW, kHalfKV)) != DS_OK) return rc;
   const int64_t n_streams = (int64_t)a.p.n_groups * a.p.B * a.p.H * a.p.n_qt;
+  if (n_streams >= (int64_t)1 << 31) return fail(DS_ERR_INVALID, "too many (group, head, q-tile) streams in one call: split the work list");
   const_cast<AttnLaunch&>(a).p.trace = g_trace_ptr;
   const_cast<AttnLaunch&>(a).p.trace_cap = g_trace_cap;
   const_cast<AttnLaunch&>(a).p.cycles = g_trace_ptr ? g_trace_ptr + (size_t)8 * g_trace_cap : nullptr;

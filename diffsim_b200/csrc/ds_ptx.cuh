@@ -25,6 +25,10 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   return t;
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -331,6 +335,18 @@ __device__ __forceinline__ float f2_hsum(uint64_t v) {
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// 2^x for two fp16 lanes in one MUFU op
+__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
+  uint32_t y;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t mul_f16x2(uint32_t a, uint32_t b) {
+  uint32_t y;
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(y) : "r"(a), "r"(b));
   return y;
 }
 
