@@ -60,6 +60,10 @@ constexpr int kTmemS = 0;        // S_A: columns [0,128), S_B: [128,256); P of t
                                  // overwrites the first 16 of its own 32 S columns
 constexpr int kTmemO = 256;      // O: [256, 256 + D_PAD)
 constexpr int kTmemOs = 416;     // O_self, packed 16-bit: [416, 416 + D_PAD/2)
+#ifndef DS_POLY_STRIDE
+#define DS_POLY_STRIDE 0
+#endif
+constexpr int kPolyStride = DS_POLY_STRIDE;   // every n-th pair of exponentials on the FMA pipe (0: none)
 constexpr int kTmemL = 496;      // softmax denominators l = P . 1 (a 16-column MMA against a constant ones tile): [496,512)
 
 template <int D>
@@ -477,9 +481,16 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           const uint64_t sl2_2 = f2_pack(sl2, sl2), nm_2 = f2_pack(-m_run, -m_run);
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
-            float x0, x1;
+            float x0, x1, e0, e1;
             f2_unpack(f2_fma(f2_pack_u(v[j], v[j + 1]), sl2_2, nm_2), x0, x1);
-            float e0 = fast_exp2(x0), e1 = fast_exp2(x1);
+            // the MUFU pipe (16 ex2 / clk / SM) is what bounds this phase: every kPolyStride-th pair is evaluated on the
+            // FMA pipe instead
+            if (kPolyStride > 0 && ((j >> 1) % (kPolyStride > 0 ? kPolyStride : 1)) == 0) {
+              exp2_poly_f2(x0, x1, e0, e1);
+            } else {
+              e0 = fast_exp2(x0);
+              e1 = fast_exp2(x1);
+            }
             if (nv < 32) {             // select, not multiply: stale columns may hold NaN
               if (j >= nv) e0 = 0.f;
               if (j + 1 >= nv) e1 = 0.f;

@@ -338,6 +338,28 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// 2^x for two fp32 lanes WITHOUT the MUFU pipe: Cody-Waite split x = j + f (j = round(x), |f| <= 0.5), a degree-3
+// minimax polynomial for 2^f (max relative error 7.5e-5 = 2^-13.7, well under the 2^-9 / 2^-12 rounding of 16-bit P)
+// on the FMA pipe, and j added straight into the exponent field.  Valid for x in [-126, 127); smaller x is clamped
+// (2^-126 is zero in 16 bits anyway), NaN inputs come out as 2^-126.
+__device__ __forceinline__ void exp2_poly_f2(float x0, float x1, float& e0, float& e1) {
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  const uint64_t x = f2_pack(x0, x1);
+  const uint64_t magic = f2_pack(12582912.0f, 12582912.0f);          // 1.5 * 2^23
+  const uint64_t r = f2_add(x, magic);                               // low mantissa bits = round(x)
+  const uint64_t jf = f2_add(r, f2_pack(-12582912.0f, -12582912.0f));
+  const uint64_t f = f2_fma(jf, f2_pack(-1.0f, -1.0f), x);           // x - j
+  uint64_t p = f2_fma(f, f2_pack(0.05517144873738289f, 0.05517144873738289f), f2_pack(0.2426108419895172f, 0.2426108419895172f));
+  p = f2_fma(p, f, f2_pack(0.6932609677314758f, 0.6932609677314758f));
+  p = f2_fma(p, f, f2_pack(0.9999281167984009f, 0.9999281167984009f));
+  float p0, p1, r0, r1;
+  f2_unpack(p, p0, p1);
+  f2_unpack(r, r0, r1);
+  e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(r0) << 23));
+  e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(r1) << 23));
+}
+
 // 2^x for two fp16 lanes in one MUFU op
 __device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
   uint32_t y;
