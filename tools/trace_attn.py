@@ -25,10 +25,10 @@ t = buf.cpu().view(8, CAP)
 names = {1: "prod wait kv_empty", 2: "prod got slot", 10: "mma qkA begin", 11: "mma qkB begin", 12: "mma qkA kv ready", 13: "mma qkB kv ready",
          14: "mma qkA issued", 15: "mma qkB issued", 20: "mma pvA begin", 21: "mma pvB begin", 22: "mma pvA p_full", 23: "mma pvB p_full",
          24: "mma pvA kv ready", 25: "mma pvB kv ready", 26: "mma pvA issued", 27: "mma pvB issued",
-         30: "sm wait sA", 31: "sm wait sB", 32: "sm got sA", 33: "sm got sB", 34: "sm max done A", 35: "sm max done B",
+         30: "sm wait sA", 31: "sm wait sB", 32: "sm got sA", 33: "sm got sB", 34: "sm chunk0 loaded, m known A", 35: "sm chunk0 loaded, m known B", 60: "sm max+vote done", 61: "sm exp done", 62: "sm next chunk landed", 50: "sm chunk0 done", 51: "sm chunk1 done", 52: "sm chunk2 done", 53: "sm chunk3 done",
          36: "sm bar passed A", 37: "sm bar passed B", 38: "sm arrived pA", 39: "sm arrived pB", 40: "epi o_full", 41: "epi done"}
 ev = []
-for slot in range(5):
+for slot in range(8):
     for x in t[slot].tolist():
         if x == 0:
             continue
