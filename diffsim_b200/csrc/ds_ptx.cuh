@@ -62,16 +62,23 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+// The suspend-time hint lets the hardware park the thread until the phase completes (it is woken by the arrival) or
+// the time limit passes: without it a waiting warp re-issues the try_wait every few dozen clocks -- 41% of all
+// instructions the v6 attention kernel executed were such spins, paid for in issue slots and, under the power cap,
+// in SM clock.
+#ifndef DS_TRYWAIT_HINT_NS
+#define DS_TRYWAIT_HINT_NS 0x989680
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)DS_TRYWAIT_HINT_NS)
       : "memory");
   return ok != 0;
 }
@@ -80,21 +87,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #define DS_WATCHDOG_NS 4000000000ull  // 4 s: a stuck pipeline traps instead of hanging the GPU
 #endif
 
-// Blocking wait with a watchdog.  try_wait suspends the thread in hardware for a
-// bounded time, so the spin is cheap; the timer is only consulted every 256 spins.
+// Blocking wait with a watchdog.  try_wait suspends the thread in hardware for a bounded time, so the spin is cheap.
+// The watchdog is a bare spin counter (three instructions): every wait is inlined into the hot path of some warp
+// role, and these kernels live or die by their instruction-cache footprint.  A stuck pipeline traps after 2^10 failed
+// try_waits (each may suspend for the hint time: seconds in total); build with -DDS_WATCHDOG_VERBOSE to have it say where.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  uint64_t t0 = 0;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 255u) == 0) {
-      uint64_t now = globaltimer_ns();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > DS_WATCHDOG_NS) {
-        printf("diffsim_b200: mbarrier watchdog: block %d thread %d bar smem+%u parity %u\n",
-               (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
-        __trap();
-      }
+    if (++spins == (1u << 10)) {
+#ifdef DS_WATCHDOG_VERBOSE
+      printf("diffsim_b200: mbarrier watchdog: block %d thread %d bar smem+%u parity %u\n", (int)blockIdx.x,
+             (int)threadIdx.x, smem_u32(bar), parity);
+#endif
+      __trap();
     }
   }
 }
@@ -279,17 +284,21 @@ __host__ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, 
 
 // Instruction descriptor for kind::f16 (fp16 / bf16 inputs, fp32 accumulate).
 // fmt: 0 = f16, 1 = bf16.  *_mn_major: 0 = K-major operand, 1 = MN-major operand.
-__host__ __device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t fmt, uint32_t M, uint32_t N,
-                                                            uint32_t a_mn_major, uint32_t b_mn_major) {
+__host__ __device__ __forceinline__ uint32_t umma_idesc_f16_ab(uint32_t fmt_a, uint32_t fmt_b, uint32_t M, uint32_t N,
+                                                               uint32_t a_mn_major, uint32_t b_mn_major) {
   uint32_t d = 0;
   d |= 1u << 4;                  // [4,6)   accumulator format: f32
-  d |= (fmt & 7u) << 7;          // [7,10)  A format
-  d |= (fmt & 7u) << 10;         // [10,13) B format
+  d |= (fmt_a & 7u) << 7;        // [7,10)  A format
+  d |= (fmt_b & 7u) << 10;       // [10,13) B format
   d |= (a_mn_major & 1u) << 15;  // [15]    A major
   d |= (b_mn_major & 1u) << 16;  // [16]    B major
   d |= ((N >> 3) & 63u) << 17;   // [17,23) N / 8
   d |= ((M >> 4) & 31u) << 24;   // [24,29) M / 16
   return d;
+}
+__host__ __device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t fmt, uint32_t M, uint32_t N, uint32_t a_mn_major,
+                                                            uint32_t b_mn_major) {
+  return umma_idesc_f16_ab(fmt, fmt, M, N, a_mn_major, b_mn_major);
 }
 
 // ---------------------------------------------------------------------------
