@@ -9,12 +9,12 @@ mkdir -p "${OUT}" "${OBJ}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
        --expt-relaxed-constexpr -cudart static ${DS_EXTRA_NVCC_FLAGS:-})
-SRCS=(ds_host.cu ds_reduce.cu ds_simmat.cu ds_attn.cu)
+SRCS=(ds_host.cu ds_reduce.cu ds_simmat.cu ds_qkv.cu ds_attn.cu)
 pids=()
 for s in "${SRCS[@]}"; do
   [ -f "${HERE}/${s}" ] || continue
   o="${OBJ}/${s%.cu}.o"
-  if [ ! -f "$o" ] || [ "${HERE}/${s}" -nt "$o" ] || [ "${HERE}/ds_ptx.cuh" -nt "$o" ] || [ "${HERE}/ds_host.h" -nt "$o" ] \
+  if [ ! -f "$o" ] || [ "${HERE}/${s}" -nt "$o" ] || [ "${HERE}/ds_ptx.cuh" -nt "$o" ] || [ "${HERE}/ds_gemm.cuh" -nt "$o" ] || [ "${HERE}/ds_host.h" -nt "$o" ] \
      || [ "${HERE}/../../include/diffsim_b200.h" -nt "$o" ]; then
     "${NVCC}" "${FLAGS[@]}" -Xptxas -v -c "${HERE}/${s}" -o "$o" 2> "${OBJ}/${s%.cu}.ptxas.log" &
     pids+=($!)

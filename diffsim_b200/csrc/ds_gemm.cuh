@@ -1,0 +1,254 @@
+// Shared tcgen05 GEMM core:  C[M,N] = A[M,K] . B[N,K]^T   (both operands K-major 16-bit, fp32 accumulation in TMEM).
+//
+// Used by K3 (N x N similarity matrix: fp32 split-K partials, ds_simmat.cu) and K4 (QKV projection of the hooked
+// attention layer: 16-bit outputs scattered into the Q / K / V caches, ds_qkv.cu).
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0      TMA producer   ring of kGemmStages x (A 128x64 + B 256x64) 128B-swizzled tiles
+//   warp 1      MMA issuer     tcgen05.mma cta_group::1, M = 128, N = 256, K = 16; also owns the TMEM allocation
+//   warps 2-5   epilogue       one TMEM lane quadrant each; TMEM -> registers -> global
+// The 512 TMEM columns hold two 128x256 fp32 accumulators, so the epilogue of work unit u overlaps the main loop of
+// unit u+1.  A work unit is (output tile, k split); units are dealt round-robin to the CTAs, tiles n-fastest so that
+// CTAs running side by side share the A tile in L2.
+//
+// Shared-memory budget of the 1-CTA shape: per 64-wide k block TMA writes 48 KB and the four MMAs read 48 KB, 96 KB
+// per 512 tensor clocks = 188 B/clk against a 128 B/clk port: this shape tops out near 68% of the tensor peak; the
+// cta_group::2 256x256 shape (half the B reads per CTA) is what lifts that and is the next step for this core.
+#pragma once
+
+#include "ds_host.h"
+#include "ds_ptx.cuh"
+
+namespace ds {
+
+constexpr int kGBM = 128, kGBN = 256, kGBK = 64;
+constexpr int kGStages = 4;
+constexpr int kGABytes = kGBM * kGBK * 2;   // 16 KB
+constexpr int kGBBytes = kGBN * kGBK * 2;   // 32 KB
+constexpr int kGStageBytes = kGABytes + kGBBytes;
+constexpr int kGThreads = 192;
+constexpr size_t kGSmemBytes = 1024 + (size_t)kGStages * kGStageBytes + 256;
+
+enum : int { GEMM_EPI_F32 = 0, GEMM_EPI_16 = 1 };
+
+struct GemmParams {
+  int M, N;                 // output extent
+  int tiles_m, tiles_n;
+  int kb_total;             // 64-wide k blocks
+  int splits, kb_per_split;
+  uint32_t idesc;
+  // GEMM_EPI_F32: part[split][M][N] fp32
+  float* part;
+  int64_t part_split_stride;
+  // GEMM_EPI_16: column n goes to out[n / cols_per_out] at column n % cols_per_out; bias (may be null) has the
+  // input dtype and N entries
+  void* out[3];
+  int64_t ld_out[3];
+  int cols_per_out;
+  const void* bias;
+};
+
+template <int EPI, bool kBf16>
+__global__ void __launch_bounds__(kGThreads, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kGStages * kGStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kGStages;
+  uint64_t* acc_full = bars + 2 * kGStages;        // [2]
+  uint64_t* acc_empty = bars + 2 * kGStages + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kGStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kGStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 4);   // one elected lane per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int n_units = tiles * p.splits;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int split = u / tiles, tile = u - split * tiles;
+        const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* a = smem + (size_t)stage * kGStageBytes;
+          mbar_arrive_expect_tx(&full[stage], kGStageBytes);
+          tma_load_2d(a, &map_a, &full[stage], kb * kGBK, tm * kGBM);
+          tma_load_2d(a + kGABytes, &map_b, &full[stage], kb * kGBK, tn * kGBN);
+          if (++stage == kGStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0, n_local = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++n_local) {
+        const int split = u / tiles;
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const uint32_t buf = n_local & 1u;
+        mbar_wait(&acc_empty[buf], ((n_local >> 1) & 1u) ^ 1u);   // the epilogue has drained this accumulator
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + buf * kGBN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * kGStageBytes);
+          const uint64_t a_desc = umma_smem_desc(a_addr, 16, 1024, UMMA_SW128);
+          const uint64_t b_desc = umma_smem_desc(a_addr + kGABytes, 16, 1024, UMMA_SW128);
+#pragma unroll
+          for (int k = 0; k < kGBK / 16; ++k) {
+            // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in 16-byte units
+            umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == kGStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+    const int quad = warp & 3;
+    uint32_t n_local = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++n_local) {
+      const int split = u / tiles, tile = u - split * tiles;
+      const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+      const uint32_t buf = n_local & 1u;
+      mbar_wait(&acc_full[buf], (n_local >> 1) & 1u);
+      tc_fence_after_sync();
+      const int row = tm * kGBM + quad * 32 + lane;
+      const int n0 = tn * kGBN;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kGBN;
+#pragma unroll 1
+      for (int c = 0; c < kGBN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_x32(t_addr + c * 32, v);
+        tmem_wait_ld();
+        const int col0 = n0 + c * 32;
+        if (row < p.M && col0 < p.N) {
+          if constexpr (EPI == GEMM_EPI_F32) {
+            float* dst = p.part + (size_t)split * p.part_split_stride + (size_t)row * p.N + col0;
+            if (col0 + 32 <= p.N && (p.N & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                  __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) dst[j] = __uint_as_float(v[j]);
+            }
+          } else {
+            // 8-column groups: 16-byte stores; N, cols_per_out are multiples of 8 (checked by the host)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int col = col0 + g * 8;
+              if (col < p.N) {
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+                if (p.bias) {
+                  const uint4 b4 = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.bias) + col));
+                  const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 bf = unpack2<kBf16>(bw[j]);
+                    f[2 * j] += bf.x;
+                    f[2 * j + 1] += bf.y;
+                  }
+                }
+                const int t = col / p.cols_per_out, cc = col - t * p.cols_per_out;
+                uint16_t* dst = static_cast<uint16_t*>(p.out[t]) + (size_t)row * p.ld_out[t] + cc;
+                *reinterpret_cast<uint4*>(dst) = make_uint4(pack2<kBf16>(f[0], f[1]), pack2<kBf16>(f[2], f[3]),
+                                                            pack2<kBf16>(f[4], f[5]), pack2<kBf16>(f[6], f[7]));
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// Host side: tensor maps + launch.  a: [M, K] with leading dimension lda (elements), b: [N, K] with ldb.
+template <int EPI>
+static int launch_gemm_tn(const void* a, int64_t M, int64_t lda, const void* b, int64_t N, int64_t ldb, int64_t K, int dtype,
+                          GemmParams p, cudaStream_t st) {
+  CUtensorMap map_a, map_b;
+  int rc;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    uint64_t str[1] = {(uint64_t)lda * 2};
+    uint32_t box[2] = {(uint32_t)kGBK, (uint32_t)kGBM};
+    if ((rc = encode_tensor_map(&map_a, dtype, 2, a, dims, str, box, 128)) != DS_OK) return rc;
+    uint64_t dimsb[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t strb[1] = {(uint64_t)ldb * 2};
+    uint32_t boxb[2] = {(uint32_t)kGBK, (uint32_t)kGBN};
+    if ((rc = encode_tensor_map(&map_b, dtype, 2, b, dimsb, strb, boxb, 128)) != DS_OK) return rc;
+  }
+  p.M = (int)M;
+  p.N = (int)N;
+  p.tiles_m = (int)((M + kGBM - 1) / kGBM);
+  p.tiles_n = (int)((N + kGBN - 1) / kGBN);
+  p.kb_total = (int)((K + kGBK - 1) / kGBK);
+  if (p.splits < 1) p.splits = 1;
+  p.kb_per_split = (p.kb_total + p.splits - 1) / p.splits;
+  p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.idesc = umma_idesc_f16(dtype == DS_BF16 ? 1u : 0u, kGBM, kGBN, 0, 0);
+  const int64_t units = (int64_t)p.tiles_m * p.tiles_n * p.splits;
+  if (units <= 0) return DS_OK;
+  if (units > INT32_MAX) return fail(DS_ERR_INVALID, "gemm: too many work units");
+  int grid = sm_count();
+  if (units < grid) grid = (int)units;
+  if (dtype == DS_BF16) {
+    DS_CUDA_TRY(cudaFuncSetAttribute(gemm_tn_kernel<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGSmemBytes));
+    gemm_tn_kernel<EPI, true><<<grid, kGThreads, kGSmemBytes, st>>>(map_a, map_b, p);
+  } else {
+    DS_CUDA_TRY(cudaFuncSetAttribute(gemm_tn_kernel<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGSmemBytes));
+    gemm_tn_kernel<EPI, false><<<grid, kGThreads, kGSmemBytes, st>>>(map_a, map_b, p);
+  }
+  DS_CUDA_TRY(cudaGetLastError());
+  return DS_OK;
+}
+
+}  // namespace ds

@@ -2,137 +2,22 @@
 //
 //   C[r,c] = sim(rows[r,:], cols[c,:])
 //
-// One tcgen05 GEMM rows x cols^T (both operands K-major, 128B-swizzled TMA tiles,
-// fp32 accumulators in TMEM), optionally split along L so that small matrices
-// still fill the 148 SMs; per-vector statistics (sum, sum of squares, min, max)
+// One tcgen05 GEMM rows x cols^T (the persistent 128x256 core of ds_gemm.cuh: K-major
+// 128B-swizzled TMA tiles, double-buffered fp32 accumulators in TMEM), split along L
+// so that the work units fill whole waves of the 148 SMs; per-vector statistics (sum, sum of squares, min, max)
 // come from one HBM pass; a finishing kernel adds the split partials in a fixed
 // order and applies the cosine / min-max-cosine normalisation.
 //
 // All-pairs form of the flat-cosine metrics: metrics/diffeats.py:202-205,
 // metrics/clip_i.py:183, metrics/dino.py:183, metrics/vgg_gram.py:81.
 // Algorithmic work: 2 * Nr * Nc * L flops.
-#include "ds_host.h"
-#include "ds_ptx.cuh"
+#include "ds_gemm.cuh"
 
 #include <float.h>
 
 #include <type_traits>
 
 namespace ds {
-
-constexpr int kGemmBM = 128;
-constexpr int kGemmBN = 128;
-constexpr int kGemmBK = 64;                                      // 64 x 2 B = one 128-byte swizzle row
-constexpr int kGemmStages = 6;
-constexpr int kGemmABytes = kGemmBM * kGemmBK * 2;               // 16 KB
-constexpr int kGemmBBytes = kGemmBN * kGemmBK * 2;               // 16 KB
-constexpr int kGemmStageBytes = kGemmABytes + kGemmBBytes;
-constexpr int kGemmThreads = 192;                                // TMA warp, MMA warp, 4 epilogue warps
-constexpr size_t kGemmSmemBytes = 1024 + (size_t)kGemmStages * kGemmStageBytes + 256;
-
-__global__ void __launch_bounds__(kGemmThreads, 1)
-simmat_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                   float* __restrict__ part, int64_t part_split_stride, int n_rows, int n_cols, int kb_total,
-                   int kb_per_split, uint32_t idesc) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kGemmStages * kGemmStageBytes);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + kGemmStages;
-  uint64_t* acc_full = bars + 2 * kGemmStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kGemmStages + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a);
-    tma_prefetch_desc(&map_b);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kGemmStages; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
-    }
-    mbar_init(acc_full, 1);
-    fence_mbar_init();
-  }
-  if (warp == 2) {
-    tmem_alloc(tmem_slot, kGemmBN);
-    tmem_relinquish();
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int m0 = blockIdx.y * kGemmBM;
-  const int n0 = blockIdx.x * kGemmBN;
-  const int kb0 = blockIdx.z * kb_per_split;
-  const int kb1 = min(kb_total, kb0 + kb_per_split);
-
-  if (warp == 0) {
-    if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&empty[stage], phase ^ 1);
-        uint8_t* a = smem + (size_t)stage * kGemmStageBytes;
-        mbar_arrive_expect_tx(&full[stage], kGemmStageBytes);
-        tma_load_2d(a, &map_a, &full[stage], kb * kGemmBK, m0);
-        tma_load_2d(a + kGemmABytes, &map_b, &full[stage], kb * kGemmBK, n0);
-        if (++stage == kGemmStages) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full[stage], phase);
-        tc_fence_after_sync();
-        const uint32_t a_addr = smem_u32(smem + (size_t)stage * kGemmStageBytes);
-        const uint64_t a_desc = umma_smem_desc(a_addr, 16, 1024, UMMA_SW128);
-        const uint64_t b_desc = umma_smem_desc(a_addr + kGemmABytes, 16, 1024, UMMA_SW128);
-#pragma unroll
-        for (int k = 0; k < kGemmBK / 16; ++k) {
-          // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in 16-byte units
-          umma_f16_ss(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-        }
-        umma_commit(&empty[stage]);
-        if (++stage == kGemmStages) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-      umma_commit(acc_full);
-    }
-  } else {
-    // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
-    mbar_wait(acc_full, 0);
-    tc_fence_after_sync();
-    const int quad = warp & 3;
-    const int row = m0 + quad * 32 + lane;
-    float* dst = part + (size_t)blockIdx.z * part_split_stride + (size_t)row * n_cols + n0;
-#pragma unroll 1
-    for (int c = 0; c < kGemmBN / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + c * 32, v);
-      tmem_wait_ld();
-      if (row < n_rows) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          int col = n0 + c * 32 + j;
-          if (col < n_cols) dst[c * 32 + j] = __uint_as_float(v[j]);
-        }
-      }
-    }
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, kGemmBN);
-}
 
 // ---------------------------------------------------------------------------
 // per-vector statistics: sum, sum of squares, min, max (one HBM pass)
@@ -259,15 +144,32 @@ struct SimmatPlan {
 
 static SimmatPlan simmat_plan(int64_t n_rows, int64_t n_cols, int64_t L) {
   SimmatPlan p;
-  p.tiles_m = (int)((n_rows + kGemmBM - 1) / kGemmBM);
-  p.tiles_n = (int)((n_cols + kGemmBN - 1) / kGemmBN);
-  p.kb_total = (int)((L + kGemmBK - 1) / kGemmBK);
-  int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
-  int64_t want = (148 + tiles - 1) / tiles;  // fill the machine once
-  if (want > 32) want = 32;
-  if (want > p.kb_total / 8) want = p.kb_total / 8;  // keep at least 8 k-blocks per split
-  if (want < 1) want = 1;
-  p.kb_per_split = (int)((p.kb_total + want - 1) / want);
+  p.tiles_m = (int)((n_rows + kGBM - 1) / kGBM);
+  p.tiles_n = (int)((n_cols + kGBN - 1) / kGBN);
+  p.kb_total = (int)((L + kGBK - 1) / kGBK);
+  // split along L: the smallest split count whose work units (tiles x splits) fill whole waves of the persistent grid
+  // to >= 95% (at least 8 k blocks per unit, at most 64 splits: the fp32 partials cost HBM traffic)
+  const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  int max_s = p.kb_total / 8;
+  if (max_s > 64) max_s = 64;
+  if (max_s < 1) max_s = 1;
+  int best_s = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= max_s; ++s) {
+    const int kps = (p.kb_total + s - 1) / s;
+    const int real_s = (p.kb_total + kps - 1) / kps;
+    const int64_t units = tiles * real_s;
+    const int64_t waves = (units + sms - 1) / sms;
+    const double eff = (double)units / (double)(waves * sms);
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best_s = real_s;
+    }
+    if (eff >= 0.95) break;
+  }
+  p.kb_per_split = (p.kb_total + best_s - 1) / best_s;
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   const int64_t quantum = 8 * kStatThreads;
   int64_t c = (L + 65535) / 65536;
@@ -340,27 +242,13 @@ int ds_simmat(const void* rows, int64_t n_rows, int64_t ld_rows, const void* col
   row_stats_finish_kernel<<<(unsigned)((n_cols + 127) / 128), 128, 0, st>>>(spart_c, p.stat_chunks, n_cols, stats_c);
   DS_CUDA_TRY(cudaGetLastError());
 
-  // GEMM
-  CUtensorMap map_a, map_b;
-  {
-    uint64_t dims[2] = {(uint64_t)L, (uint64_t)n_rows};
-    uint64_t str[1] = {(uint64_t)ld_rows * 2};
-    uint32_t box[2] = {(uint32_t)kGemmBK, (uint32_t)kGemmBM};
-    rc = encode_tensor_map(&map_a, dtype, 2, rows, dims, str, box, 128);
-    if (rc != DS_OK) return rc;
-    uint64_t dimsb[2] = {(uint64_t)L, (uint64_t)n_cols};
-    uint64_t strb[1] = {(uint64_t)ld_cols * 2};
-    uint32_t boxb[2] = {(uint32_t)kGemmBK, (uint32_t)kGemmBN};
-    rc = encode_tensor_map(&map_b, dtype, 2, cols, dimsb, strb, boxb, 128);
-    if (rc != DS_OK) return rc;
-  }
-  DS_CUDA_TRY(cudaFuncSetAttribute(simmat_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
-  const uint32_t idesc = umma_idesc_f16(dtype == DS_BF16 ? 1u : 0u, kGemmBM, kGemmBN, 0, 0);
-  dim3 grid(p.tiles_n, p.tiles_m, p.splits);
-  simmat_gemm_kernel<<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, part, (int64_t)n_rows * n_cols,
-                                                               (int)n_rows, (int)n_cols, p.kb_total, p.kb_per_split,
-                                                               idesc);
-  DS_CUDA_TRY(cudaGetLastError());
+  // GEMM: fp32 partials part[split][row][col]
+  GemmParams gp = {};
+  gp.splits = p.splits;
+  gp.part = part;
+  gp.part_split_stride = (int64_t)n_rows * n_cols;
+  rc = launch_gemm_tn<GEMM_EPI_F32>(rows, n_rows, ld_rows, cols, n_cols, ld_cols, L, dtype, gp, st);
+  if (rc != DS_OK) return rc;
 
   const int64_t fblocks = ((n_cols + 255) / 256) * n_rows;
   if (fblocks > 0x7fffffffLL) return fail(DS_ERR_INVALID, "ds_simmat: matrix too large");

@@ -262,6 +262,54 @@ def simmat(rows: torch.Tensor, cols: Optional[torch.Tensor] = None, similarity="
 
 
 # --------------------------------------------------------------------------------------
+# K4: QKV projection of the hooked layer
+# --------------------------------------------------------------------------------------
+def qkv_project(hidden: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, n_outputs: int = 3,
+                out: Optional[Sequence[torch.Tensor]] = None) -> Tuple[torch.Tensor, ...]:
+    """hidden (..., C_in) x weight (n_out, C_in)^T (+ bias) -> n_outputs tensors (..., n_out / n_outputs).
+
+    The capture step of the reference on the hook's input: attn.to_q / to_k / to_v (diffsim/hacked_attn.py:61-69,
+    weight = the three nn.Linear weights stacked along dim 0) or DiT's fused module.qkv (diffsim/diffsim_dit.py:21,
+    n_outputs = 1: one packed (..., 3C) tensor).  fp32 accumulation on tcgen05, one rounding to the input dtype.
+    `out`: optional pre-allocated outputs (row stride may exceed the column count, e.g. slices of a cache)."""
+    import ctypes as C
+
+    lib = N.load()
+    dev = _need_cuda(hidden, weight)
+    if hidden.dtype != weight.dtype or (bias is not None and bias.dtype != hidden.dtype):
+        raise RuntimeError("hidden, weight and bias must share one 16-bit dtype")
+    c_in = hidden.shape[-1]
+    if weight.dim() != 2 or weight.shape[1] != c_in or weight.stride(1) != 1:
+        raise RuntimeError(f"weight must be (n_out, {c_in}) with contiguous rows (nn.Linear layout)")
+    n_out = weight.shape[0]
+    if n_out % n_outputs:
+        raise RuntimeError("n_out must be a multiple of n_outputs")
+    cols = n_out // n_outputs
+    h2 = hidden.reshape(-1, c_in)
+    if h2.stride(1) != 1:
+        h2 = h2.contiguous()
+    rows = h2.shape[0]
+    if out is None:
+        out = [torch.empty(hidden.shape[:-1] + (cols,), dtype=hidden.dtype, device=dev) for _ in range(n_outputs)]
+    if len(out) != n_outputs:
+        raise RuntimeError(f"expected {n_outputs} output tensors")
+    o2 = []
+    for o in out:
+        if o.dtype != hidden.dtype or o.device != dev or o.shape[-1] != cols or o.stride(-1) != 1 or o.numel() != rows * cols:
+            raise RuntimeError("outputs must be (..., n_out / n_outputs) tensors of the input dtype on the input device")
+        o_rows = o.reshape(-1, cols) if o.is_contiguous() else o.view(-1, cols)
+        o2.append(o_rows)
+    ptrs = (C.c_void_p * n_outputs)(*[o.data_ptr() for o in o2])
+    lds = (C.c_int64 * n_outputs)(*[o.stride(0) for o in o2])
+    with torch.cuda.device(dev):
+        N.check(lib.ds_qkv_project(h2.data_ptr(), rows, h2.stride(0), c_in, weight.data_ptr(), weight.stride(0),
+                                   bias.data_ptr() if bias is not None else None, n_out, cols, ptrs, lds,
+                                   _dtype_code(hidden), _stream(dev)))
+    _count(1)
+    return tuple(out)
+
+
+# --------------------------------------------------------------------------------------
 # decisions
 # --------------------------------------------------------------------------------------
 def twoafc(ab: torch.Tensor, ac: torch.Tensor, similarity="cosine") -> Tuple[torch.Tensor, torch.Tensor]:

@@ -131,6 +131,76 @@ class HostTripletScorer:
         return int(out[0]), int(out[1])
 
 
+def project_cache(hidden: torch.Tensor, weight: torch.Tensor, heads: int, bias: Optional[torch.Tensor] = None,
+                  out: Optional[QKVCache] = None) -> QKVCache:
+    """Hook inputs -> Q/K/V cache: hidden (N,B,S,C) x [W_q; W_k; W_v] (3C', C) -> three (N,B,H,S,D) views over
+    (N,B,S,C') memory, the capture step of the reference (diffsim/hacked_attn.py:61-69,74-77) for N images in one
+    tcgen05 GEMM (ops.qkv_project).  `out`: a cache to fill (its first N images)."""
+    n, B, S, _ = hidden.shape
+    c_out = weight.shape[0] // 3
+    D = c_out // heads
+    if out is None:
+        out = QKVCache.empty(n, B, heads, S, D, hidden.dtype, hidden.device)
+    mems = [m[:n] for m in out.memory()]
+    ops.qkv_project(hidden, weight, bias, 3, out=mems)
+    return out.slice(0, n) if out.n_images != n else out
+
+
+class HostHiddenTripletScorer:
+    """End-to-end scorer at the HOOK-INPUT boundary: pinned host hidden states of the target attention layer
+    (what `register_forward_pre_hook` hands the reference's hook, diffsim/diffsim.py:43-56) -> chunked,
+    double-buffered H2D copies on a copy stream -> QKV projection (K4) + fused AAS scoring (K1) on the compute
+    stream -> decision counts back on the host.  A third of the bytes of HostTripletScorer's Q/K/V boundary.
+
+    Triplet t uses images (3t, 3t+1, 3t+2) of the host buffer (reference, left, right)."""
+
+    def __init__(self, shape: Tuple[int, int, int, int], weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                 dtype=torch.float16, device="cuda", chunk_triplets: int = 96, similarity: str = "cosine"):
+        self.shape, self.dtype, self.device = shape, dtype, torch.device(device)
+        self.chunk = chunk_triplets
+        self.similarity = similarity
+        self.weight, self.bias = weight, bias
+        B, H, S, D = shape
+        c_in = weight.shape[1]
+        self.hid = [torch.empty(3 * chunk_triplets, B, S, c_in, dtype=dtype, device=device) for _ in range(2)]
+        self.cache = QKVCache.empty(3 * chunk_triplets, B, H, S, D, dtype, device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.copied = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.trips = torch.arange(3 * chunk_triplets, dtype=torch.int32, device=device).view(-1, 3)
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def score(self, host_hidden: torch.Tensor, n_triplets: int):
+        """host_hidden: (>= 3 n_triplets, B, S, C) pinned host tensor.  Returns (correct, correct_2x) as Python ints
+        (one device->host read at the end)."""
+        dev = self.device
+        H = self.shape[1]
+        compute = torch.cuda.current_stream(dev)
+        totals = torch.zeros(2, dtype=torch.int32, device=dev)
+        n_chunks = (n_triplets + self.chunk - 1) // self.chunk
+        for c in range(n_chunks):
+            t0, t1 = c * self.chunk, min(n_triplets, (c + 1) * self.chunk)
+            nb = c % 2
+            n_img = 3 * (t1 - t0)
+            with torch.cuda.stream(self.copy_stream):
+                if c >= 2:
+                    self.copy_stream.wait_event(self.consumed[nb])
+                src = host_hidden[3 * t0: 3 * t1]
+                self.hid[nb][:n_img].copy_(src, non_blocking=True)
+                self.h2d_bytes += src.numel() * src.element_size()
+                self.copied[nb].record(self.copy_stream)
+            compute.wait_event(self.copied[nb])
+            cache = project_cache(self.hid[nb][:n_img], self.weight, H, self.bias, out=self.cache)
+            self.consumed[nb].record(compute)   # the hidden-state buffer is free once the projection has read it
+            _, _, counts, _ = ops.aas_triplets(cache.q, cache.k, cache.v, self.trips[: t1 - t0], self.similarity,
+                                               want_flags=False)
+            totals += counts
+        out = totals.cpu()  # the step's result read: device -> host
+        self.d2h_bytes += out.numel() * out.element_size()
+        return int(out[0]), int(out[1])
+
+
 # --------------------------------------------------------------------------------------------------------
 # all-pairs retrieval
 # --------------------------------------------------------------------------------------------------------

@@ -82,6 +82,11 @@ class SynthModel:
             return qkv[0], qkv[1], qkv[2]
         raise ValueError(layout)
 
+    def linear_weights(self, dtype=torch.float16) -> torch.Tensor:
+        """[W_q; W_k; W_v] stacked along dim 0 in nn.Linear layout ([out, in], 3C x C): the to_q / to_k / to_v weights
+        of the hooked layer (diffsim/hacked_attn.py:61-69) as the projection kernel takes them."""
+        return torch.cat([self.Wq.t(), self.Wk.t(), self.Wv.t()], dim=0).to(dtype).contiguous()
+
     def image(self, base: torch.Tensor, alpha: float, dtype=torch.float16, layout: str = "sd",
               generator: Optional[torch.Generator] = None):
         return self.qkv(self.hidden(base, alpha, generator), dtype, layout)
@@ -179,3 +184,30 @@ def device_cache(B: int, H: int, S: int, D: int, n_images: int, dtype=torch.floa
         mems[1][i0:i1] = (h @ Wk).to(dtype)
         mems[2][i0:i1] = (h @ Wv).to(dtype)
     return tuple(m.view(n_images, B, S, H, D).permute(0, 1, 3, 2, 4) for m in mems)
+
+
+def device_hidden(B: int, H: int, S: int, D: int, n_images: int, dtype=torch.float16, device="cuda", seed: int = 0,
+                  n_bases: int = 64, alpha_lo: float = 0.3, alpha_hi: float = 0.99, pin_host: bool = False):
+    """Hook-INPUT form of device_cache: hidden states (N,B,S,C) of n_images synthetic images (same recipe) plus the
+    stacked projection weight [W_q; W_k; W_v] (3C, C) in nn.Linear layout, both in `dtype`.  With pin_host the hidden
+    states are returned in pinned host memory (generated on the device in chunks, copied back)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    C = H * D
+    std = 1.0 / math.sqrt(C)
+    Wq = torch.randn(C, C, generator=g, device=device) * (std * 2.2)
+    Wk = torch.randn(C, C, generator=g, device=device) * (std * 2.2)
+    Wv = torch.randn(C, C, generator=g, device=device) * std
+    weight = torch.cat([Wq.t(), Wk.t(), Wv.t()], dim=0).to(dtype).contiguous()
+    bases = torch.randn(n_bases, 1, S, C, generator=g, device=device).repeat(1, B, 1, 1)
+    if B > 1:
+        bases[:, 1:] += 0.1 * torch.randn(n_bases, B - 1, S, C, generator=g, device=device)
+    out = torch.empty(n_images, B, S, C, dtype=dtype, device="cpu" if pin_host else device, pin_memory=pin_host)
+    chunk = 64
+    for i0 in range(0, n_images, chunk):
+        i1 = min(n_images, i0 + chunk)
+        idx = (torch.arange(i0, i1, device=device) // 3) % n_bases
+        alpha = alpha_lo + (alpha_hi - alpha_lo) * torch.rand(i1 - i0, 1, 1, 1, generator=g, device=device)
+        alpha[(torch.arange(i0, i1, device=device) % 3) == 0] = 1.0  # image 3t is the clean reference
+        h = alpha * bases[idx] + torch.sqrt(1 - alpha * alpha) * torch.randn(i1 - i0, B, S, C, generator=g, device=device)
+        out[i0:i1].copy_(h.to(dtype))
+    return out, weight

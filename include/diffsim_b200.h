@@ -208,6 +208,26 @@ int ds_simmat(const void* rows, int64_t n_rows, int64_t ld_rows,
               void* ws, size_t ws_bytes, void* stream);
 size_t ds_simmat_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t L);
 
+/* ---- K4: QKV projection of the hooked layer ------------------------------ */
+
+/*
+ * [out_0 | out_1 | out_2][r, :] = hidden[r, :] . weight^T (+ bias),  r < n_rows
+ * The capture step of the reference, on the hook's input: attn.to_q / to_k / to_v
+ * (diffsim/hacked_attn.py:61-69; the head split of :74-77 is a view of the output rows)
+ * and DiT's fused module.qkv(x) (diffsim/diffsim_dit.py:21-23).
+ * hidden: [n_rows, c_in] (n_rows = images * B * S), weight: [n_out, c_in] in nn.Linear
+ * layout -- for separate to_q/to_k/to_v modules the three weights stacked along dim 0 --,
+ * bias: [n_out] or null, all of `dtype` (DS_F16 | DS_BF16).  Output column n goes to
+ * out[n / cols_per_out] at column n % cols_per_out, row stride ld_out[.] elements:
+ * SD: n_out = 3C, cols_per_out = C, three (rows, C) tensors = the Q / K / V caches;
+ * DiT: cols_per_out = n_out = 3C, one packed (rows, 3C) tensor.
+ * fp32 accumulation, bias added in fp32, one rounding to `dtype`.  No workspace.
+ */
+int ds_qkv_project(const void* hidden, int64_t n_rows, int64_t ld_hidden, int64_t c_in,
+                   const void* weight, int64_t ld_weight, const void* bias,
+                   int64_t n_out, int64_t cols_per_out,
+                   void* const* out, const int64_t* ld_out, int dtype, void* stream);
+
 /* ---- decisions ---------------------------------------------------------- */
 
 /*

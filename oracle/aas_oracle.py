@@ -187,3 +187,32 @@ def reference_pair_score(qa, ka, va, qb, kb, vb, mode: str = "cosine") -> torch.
     else:
         s_ab, s_ba = F.mse_loss(a_on_b, self_a), F.mse_loss(b_on_a, self_b)
     return (s_ab + s_ba) / 2
+
+
+# ----------------------------------------------------------------------------------------------------
+# QKV projection of the hooked layer (diffsim/hacked_attn.py:61-69,74-77; diffsim/diffsim_dit.py:21-23)
+# ----------------------------------------------------------------------------------------------------
+def project_qkv(hidden: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, n_outputs: int = 3,
+                round_to: Optional[torch.dtype] = None):
+    """y = hidden @ weight^T (+ bias) in float64 (weight in nn.Linear layout [n_out, C_in]; for separate
+    to_q / to_k / to_v modules the three weights stacked along dim 0), split into n_outputs column blocks.
+    round_to: round the result to that dtype (what an fp16 / bf16 nn.Linear returns) and hand it back as such."""
+    y = torch.matmul(hidden.to(torch.float64), weight.to(torch.float64).t())
+    if bias is not None:
+        y = y + bias.to(torch.float64)
+    if round_to is not None:
+        y = y.to(round_to)
+    return tuple(y.chunk(n_outputs, dim=-1))
+
+
+def reference_capture(hidden: torch.Tensor, wq: torch.Tensor, wk: torch.Tensor, wv: torch.Tensor, heads: int):
+    """T2: the reference's capture lines in the native dtype -- attn.to_q / to_k / to_v on the hook input and the
+    head-split views (diffsim/hacked_attn.py:61-69,74-77); bias-free as SD's attn1 projections are."""
+    import torch.nn.functional as F
+
+    B, S, _ = hidden.shape
+    out = []
+    for w in (wq, wk, wv):
+        y = F.linear(hidden, w)
+        out.append(y.view(B, S, heads, y.shape[-1] // heads).transpose(1, 2))
+    return tuple(out)

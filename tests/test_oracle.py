@@ -124,3 +124,24 @@ def test_matrix_is_the_pair_formula():
         assert dm[i, i].item() == pytest.approx(1.0, abs=1e-12)
         for j in range(3):
             assert S[i, j].item() == pytest.approx(O.aas_pair_score(*imgs[i], *imgs[j]), rel=1e-12)
+
+
+def test_projection_oracle_matches_the_reference_capture_lines():
+    """oracle.project_qkv (float64) against the reference's own capture arithmetic -- attn.to_q / to_k / to_v +
+    head-split views, diffsim/hacked_attn.py:61-69,74-77 -- in fp32 (1e-4 of max(|y|, 0.05)) and fp16 (1.5e-3: one fp16 ulp on top)."""
+    from diffsim_b200 import synth
+
+    m = synth.SynthModel(2, 4, 64, 40, seed=2334)
+    g = torch.Generator().manual_seed(1)
+    hidden = m.hidden(m.new_base(g), 0.7, g)
+    for dtype, tol in ((torch.float32, 1e-4), (torch.float16, 1.5e-3)):
+        w = m.linear_weights(dtype)
+        C = w.shape[1]
+        h = hidden.to(dtype)
+        ref = O.reference_capture(h, w[:C], w[C:2 * C], w[2 * C:], heads=4)
+        got = O.project_qkv(h, w)
+        for r, o in zip(ref, got):
+            o = o.view(2, 64, 4, 40).transpose(1, 2)
+            assert r.shape == (2, 4, 64, 40) and r.stride()[-1] == 1
+            err = ((r.double() - o).abs() / o.abs().clamp_min(0.05)).max().item()
+            assert err < tol, (dtype, err)

@@ -58,3 +58,17 @@ for n, L in ((512, 655360), (2032, 65536), (2032, 655360)):
 f = torch.randn(2032, 65536, device="cuda", dtype=torch.float16)
 ms = timeit(lambda: (f @ f.T), iters=2, warmup=1)
 print(f"[torch matmul fp16 2032x2032x65536] {ms:.2f} ms {2 * 2032 * 2032 * 65536 / ms / 1e9:.0f} TFLOP/s")
+del f
+
+# K4: QKV projection of the hooked layer, SD-1.5 up0: rows = images x 512, C = 1280 -> 3 x 1280
+for n_img in (96, 768):
+    hid, w = synth.device_hidden(2, 8, 256, 160, n_img, torch.float16, "cuda")
+    outs = [torch.empty(n_img, 2, 256, 1280, dtype=torch.float16, device="cuda") for _ in range(3)]
+    ms = timeit(lambda: ops.qkv_project(hid, w, None, 3, out=outs), iters=5, warmup=2)
+    fl = 2 * n_img * 512 * 1280 * 3840
+    print(f"[K4 qkv_project] {n_img} images (rows {n_img * 512} x 1280 -> 3840): {ms:.3f} ms  {fl / ms / 1e9:.0f} TFLOP/s  "
+          f"{n_img / ms * 1e3:.0f} images/s", flush=True)
+    h2 = hid.view(-1, 1280)
+    ms = timeit(lambda: h2 @ w.t(), iters=5, warmup=2)
+    print(f"[torch matmul same shape] {ms:.3f} ms  {fl / ms / 1e9:.0f} TFLOP/s", flush=True)
+    del hid, outs, h2
