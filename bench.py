@@ -17,8 +17,11 @@ The JSON line also carries
                 on the launching stream) vs the measured bf16 tensor peak of MEASURED_PEAKS.json
   cpu_baseline  the reference's own torch lines (4 SDPA + 2 cosine per pair, diffsim/diffsim.py:177-197) on the
                 host cores, bounded sample
-  e2e           the same metric through HostTripletScorer: pinned host Q/K/V -> H2D copies inside the timed
-                region -> fused kernels -> decision counts read back
+  e2e           the same metric through the hook-input boundary (HostHiddenTripletScorer): pinned host hidden states
+                of the hooked layer -> H2D copies inside the timed region -> QKV projection (K4) -> fused AAS kernels
+                (K1) -> decision counts read back.  e2e_qkv_boundary: the same with host Q/K/V (3x the bytes).
+The CPU legs (cpu_baseline, --impl reference) time what the reference executes per pair at that boundary: the capture
+projections of both images (6 x F.linear, diffsim/hacked_attn.py:61-69) + 4 SDPA + 2 cosine (diffsim/diffsim.py:177-197).
 """
 import argparse
 import json
@@ -33,6 +36,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SHAPE = (2, 8, 256, 160)  # SD-1.5 512^2 up_blocks layer 0
+DRAM_BYTES_PER_TRIPLET = (8.493380e9 + 9.360384e6) / 512  # ncu --set full, profiles/r1t_attn_ncu_summary.txt
 WORKLOAD = "nights_2afc_triplets_sd15_512_up0_cosine"
 METRIC = "scored_pairs_per_sec"
 
@@ -130,6 +134,9 @@ def physical_gpu_index(local_rank: int) -> int:
 # CPU baseline: the reference's arithmetic on the host cores
 # ------------------------------------------------------------------------------------------------------
 def cpu_reference_pairs_per_sec(n_pairs: int, threads: int, dtype_name: str = "float16", repeats: int = 1):
+    """The reference's work per scored pair at the hook-input boundary, on the host cores: for each of the two images
+    attn.to_q / to_k / to_v on the hook input + head-split views (diffsim/hacked_attn.py:61-69,74-77 -- the reference
+    re-runs the capture for every diffsim(A,B) call), then 4 SDPA + 2 cosine (diffsim/diffsim.py:177-197)."""
     import torch
     from diffsim_b200 import synth
     from oracle import aas_oracle as O
@@ -137,21 +144,28 @@ def cpu_reference_pairs_per_sec(n_pairs: int, threads: int, dtype_name: str = "f
     torch.set_num_threads(threads)
     dtype = getattr(torch, dtype_name)
     B, H, S, D = SHAPE
+    C = H * D
     m = synth.SynthModel(B, H, S, D, seed=2334)
     n_img = 8  # a small pool of distinct images, cycled: the cost per pair does not depend on the values
     g = torch.Generator().manual_seed(7)
     base = m.new_base(g)
-    imgs = [m.image(base, 0.5 + 0.06 * i, dtype, "sd", g) for i in range(n_img)]
-    # warm-up
-    for i in range(2):
-        O.reference_pair_score(*imgs[0], *imgs[1])
+    hid = [m.hidden(base, 0.5 + 0.06 * i, g).to(dtype) for i in range(n_img)]
+    w = m.linear_weights(dtype)
+    wq, wk, wv = w[:C], w[C:2 * C], w[2 * C:]
+
+    def pair(a, b):
+        qa, ka, va = O.reference_capture(hid[a], wq, wk, wv, H)
+        qb, kb, vb = O.reference_capture(hid[b], wq, wk, wv, H)
+        return O.reference_pair_score(qa, ka, va, qb, kb, vb)
+
+    for i in range(2):  # warm-up
+        pair(0, 1)
     best = float("inf")
     for _ in range(repeats):
         t0 = time.perf_counter()
         acc = 0.0
         for p in range(n_pairs):
-            a, b = imgs[p % n_img], imgs[(p + 1 + p // n_img) % n_img]
-            acc += float(O.reference_pair_score(*a, *b))
+            acc += float(pair(p % n_img, (p + 1 + p // n_img) % n_img))
         best = min(best, time.perf_counter() - t0)
     return n_pairs / best, best
 
@@ -178,8 +192,10 @@ def run_reference_arm(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "shape_BHSD": list(SHAPE), "similarity": "cosine",
-                   "note": "reference arithmetic (4x F.scaled_dot_product_attention + 2x F.cosine_similarity per pair, "
-                           "diffsim/diffsim.py:177-197) in torch %s on the host cores; trunk not included" % torch.__version__},
+                   "boundary": "hook input (hidden states of the target attn1 layer) -> pair score",
+                   "note": "reference arithmetic per pair (6x F.linear capture projections, hacked_attn.py:61-69; 4x "
+                           "F.scaled_dot_product_attention + 2x F.cosine_similarity, diffsim/diffsim.py:177-197) in torch %s "
+                           "on the host cores; VAE / UNet trunk not included" % torch.__version__},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
                          "sample": f"{sample} pairs per step, fp16, torch.set_num_threads({threads})"},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -205,6 +221,8 @@ def main():
     ap.add_argument("--dtype", default="float16", choices=["float16", "bfloat16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="bracket the timed device-resident steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -240,6 +258,7 @@ def main():
     trips = torch.arange(3 * T, dtype=torch.int32, device=dev).view(T, 3)
     pairs_per_step = 2 * T
     attn_per_step = 7 * T  # ref self + 2 cross, left self + cross, right self + cross
+    resident_gib = 3 * T * cache.bytes_per_image / 2**30
 
     def step():
         return scoring.score_triplets(cache, trips, "cosine")
@@ -253,11 +272,15 @@ def main():
     launches0 = ops.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if args.profiler_range:
+        torch.cuda.cudart().cudaProfilerStart()
     e0.record()
     for _ in range(args.steps):
         ab, ac, counts, flags = step()
     e1.record()
     barrier()
+    if args.profiler_range:
+        torch.cuda.cudart().cudaProfilerStop()
     launches = ops.LAUNCHES - launches0
     kern_ms, kern_n = ops.profile_collect()
     ops.profile_enable(False)
@@ -283,7 +306,10 @@ def main():
     roofline = {
         "kernel": "aas_attn_kernel<160,f16,cos> (fused QK^T -> online softmax -> PV -> cosine partials; tcgen05/TMEM/TMA)",
         "bound": "tensor", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
-        "frac": (achieved_tflops / peak) if achieved_tflops else None, "traffic": None,
+        "frac": (achieved_tflops / peak) if achieved_tflops else None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full capture of the same workload at
+        # 512 triplets per launch (profiles/r1t_attn_ncu_summary.txt), scaled to this launch's triplet count
+        "traffic": DRAM_BYTES_PER_TRIPLET * T, "traffic_algorithmic": 3 * T * cache.bytes_per_image,
         "peak_source": peaks["source"] + (", sustained bf16 figure (kernel timed inside a long power-capped run)"
                                           if sustained else ", burst bf16 figure"),
         "frac_of_burst_peak": (achieved_tflops / peaks["bf16_tflops"]) if achieved_tflops else None,
@@ -294,33 +320,75 @@ def main():
 
     # ---- end to end: host buffers, H2D inside the timed region -------------------------------------------------
     e2e = None
+    extra = {}
     if not args.no_e2e:
         Te = args.e2e_triplets
-        host = scoring.QKVCache.empty(3 * Te, B, H, S, D, dtype, "cpu", pin=True)
-        for hm, dm in zip(host.memory(), cache.memory()):
-            hm.copy_(dm[: 3 * Te])
-        scorer = scoring.HostTripletScorer(SHAPE, dtype, dev, chunk_triplets=96)
-        scorer.score(host, Te)  # warm-up
-        scorer.score(host, Te)
-        scorer.h2d_bytes = scorer.d2h_bytes = 0
-        barrier()
-        t0 = time.perf_counter()
+
+        def timed(fn, n_steps):
+            barrier()
+            t0 = time.perf_counter()
+            e0.record()
+            for _ in range(n_steps):
+                out = fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            wall = time.perf_counter() - t0
+            te = torch.tensor([max(wall * 1e3, e0.elapsed_time(e1))], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            return float(te.item()), out
+
+        # (1) the headline: hook-input boundary.  Pinned host hidden states -> K4 projection -> K1 scoring
+        del cache, q, k, v
+        torch.cuda.empty_cache()
+        hid_host, weight = synth.device_hidden(B, H, S, D, 3 * Te, dtype, dev, seed=2000 + rank, pin_host=True)
+        hscorer = scoring.HostHiddenTripletScorer(SHAPE, weight, None, dtype, dev, chunk_triplets=96)
+        hscorer.score(hid_host, Te)  # warm-up
+        hscorer.score(hid_host, Te)
+        hscorer.h2d_bytes = hscorer.d2h_bytes = 0
+        l0 = ops.LAUNCHES
+        ms_e, c_e2e = timed(lambda: hscorer.score(hid_host, Te), args.e2e_steps)
+        e2e = {"value": world * 2 * Te * args.e2e_steps / (ms_e * 1e-3), "unit": "pairs/s",
+               "h2d_bytes_per_step": hscorer.h2d_bytes // args.e2e_steps,
+               "d2h_bytes_per_step": hscorer.d2h_bytes // args.e2e_steps,
+               "triplets_per_step_per_gpu": Te, "steps": args.e2e_steps, "gpu_launches": ops.LAUNCHES - l0,
+               "boundary": "hook input: hidden states (B,S,C) of the target attn1 layer, 3 images per triplet",
+               "api": "diffsim_b200.scoring.HostHiddenTripletScorer.score (pinned host hidden states -> ds_qkv_project -> "
+                      "ds_aas_triplets -> counts)",
+               "h2d_gbs": hscorer.h2d_bytes / (ms_e * 1e-3) / 1e9, "correct": c_e2e[0]}
+        # K4 alone on the resident copy of the same hidden states (secondary roofline)
+        hid_dev = hid_host[: 3 * min(Te, 256)].to(dev)
+        outs = [torch.empty(hid_dev.shape[:-1] + (H * D,), dtype=dtype, device=dev) for _ in range(3)]
+        for _ in range(3):
+            ops.qkv_project(hid_dev, weight, None, 3, out=outs)
         e0.record()
-        for _ in range(args.e2e_steps):
-            c_e2e = scorer.score(host, Te)
+        for _ in range(10):
+            ops.qkv_project(hid_dev, weight, None, 3, out=outs)
         e1.record()
         torch.cuda.synchronize(dev)
-        wall = time.perf_counter() - t0
-        te = torch.tensor([max(wall * 1e3, e0.elapsed_time(e1))], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * 2 * Te * args.e2e_steps / (float(te.item()) * 1e-3), "unit": "pairs/s",
-               "h2d_bytes_per_step": scorer.h2d_bytes // args.e2e_steps,
-               "d2h_bytes_per_step": scorer.d2h_bytes // args.e2e_steps,
-               "triplets_per_step_per_gpu": Te, "steps": args.e2e_steps,
-               "api": "diffsim_b200.scoring.HostTripletScorer.score (pinned host Q/K/V -> ds_aas_triplets)",
-               "correct": c_e2e[0]}
-        del host, scorer
+        k4_ms = e0.elapsed_time(e1) / 10
+        k4_fl = 2.0 * hid_dev.shape[0] * B * S * (H * D) * (3 * H * D)
+        extra["roofline_k4"] = {"kernel": "gemm_tn_kernel<EPI_16> (QKV projection, tcgen05 128x256 tiles)", "bound": "tensor",
+                                "achieved": k4_fl / (k4_ms * 1e-3) / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                                "frac": k4_fl / (k4_ms * 1e-3) / 1e12 / peaks["bf16_tflops"], "traffic": None,
+                                "flops_per_launch": k4_fl, "ms_per_launch": k4_ms, "images_per_launch": hid_dev.shape[0]}
+        del hid_dev, outs
+        # (2) for comparison: the Q/K/V boundary (what round-1's first bench lines reported)
+        dcache = scoring.project_cache(hid_host[: 3 * Te].to(dev), weight, H)
+        host = scoring.QKVCache.empty(3 * Te, B, H, S, D, dtype, "cpu", pin=True)
+        for hm, dm in zip(host.memory(), dcache.memory()):
+            hm.copy_(dm)
+        del dcache
+        scorer = scoring.HostTripletScorer(SHAPE, dtype, dev, chunk_triplets=96)
+        scorer.score(host, Te)  # warm-up
+        scorer.h2d_bytes = scorer.d2h_bytes = 0
+        ms_q, c_q = timed(lambda: scorer.score(host, Te), args.e2e_steps)
+        extra["e2e_qkv_boundary"] = {"value": world * 2 * Te * args.e2e_steps / (ms_q * 1e-3), "unit": "pairs/s",
+                                     "h2d_bytes_per_step": scorer.h2d_bytes // args.e2e_steps,
+                                     "d2h_bytes_per_step": scorer.d2h_bytes // args.e2e_steps,
+                                     "api": "diffsim_b200.scoring.HostTripletScorer.score (pinned host Q/K/V -> ds_aas_triplets)",
+                                     "correct": c_q[0]}
+        del host, scorer, hscorer, hid_host
 
     # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------------------------
     cpu = None
@@ -328,8 +396,8 @@ def main():
         threads = os.cpu_count() or 1
         v_cpu, t_cpu = cpu_reference_pairs_per_sec(args.cpu_pairs, threads)
         cpu = {"value": v_cpu, "unit": "pairs/s", "cores": threads, "kind": "port",
-               "sample": f"{args.cpu_pairs} pairs of the same shape, fp16, reference torch calls "
-                         f"(4 SDPA + 2 cosine per pair), {t_cpu:.1f} s"}
+               "sample": f"{args.cpu_pairs} pairs of the same shape, fp16, reference torch calls per pair at the hook-input "
+                         f"boundary (6 F.linear capture projections + 4 SDPA + 2 cosine), {t_cpu:.1f} s"}
 
     if world > 1:
         dist.barrier()
@@ -341,10 +409,13 @@ def main():
             "config": {"workload": WORKLOAD, "shape_BHSD": list(SHAPE), "triplets_per_step_per_gpu": T,
                        "pairs_per_step_per_gpu": pairs_per_step, "attentions_per_triplet": 7,
                        "similarity": "cosine", "parallelism": f"pairs sharded over {world} rank(s), no data-path collective",
-                       "l2": f"inputs {3 * T * cache.bytes_per_image / 2**30:.1f} GiB per step > 126 MB L2 (no flush needed)"},
+                       "value_boundary": "Q/K/V of the hooked layer resident in HBM (K1 only); e2e adds the hook-input "
+                                         "boundary: H2D of hidden states + K4 projection",
+                       "l2": f"inputs {resident_gib:.1f} GiB per step > 126 MB L2 (no flush needed)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": sampler.summary(), "correct_2afc": correct,
         }
+        line.update(extra)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
