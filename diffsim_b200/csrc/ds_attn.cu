@@ -60,6 +60,15 @@ constexpr int kTmemS = 0;        // S_A: columns [0,128), S_B: [128,256); P of t
                                  // overwrites the first 16 of its own 32 S columns
 constexpr int kTmemO = 256;      // O: [256, 256 + D_PAD)
 constexpr int kTmemOs = 416;     // O_self, packed 16-bit: [416, 416 + D_PAD/2)
+#ifndef DS_PV_UNROLL
+#define DS_PV_UNROLL 0
+#endif
+#ifndef DS_WARP_ARRIVE
+#define DS_WARP_ARRIVE 0     // 1: one elected lane per warp arrives on p_full / o_empty (16 / 8 arrivals instead of 512 / 256)
+#endif
+#ifndef DS_MMA_WAIT
+#define DS_MMA_WAIT 0        // waits of the MMA-issuing thread: 0 suspend hint, 1 try_wait without hint, 2 test_wait spin
+#endif
 #ifndef DS_POLY_STRIDE
 #define DS_POLY_STRIDE 0
 #endif
@@ -175,6 +184,19 @@ __device__ __forceinline__ void for_each_group(const AttnParams& p, F&& f) {
   }
 }
 
+// waits of the single MMA-issuing thread: it is the latency-critical serial resource of the pipeline, and one spinning
+// thread costs next to nothing in issue slots
+__device__ __forceinline__ void mma_wait(uint64_t* bar, uint32_t parity) {
+#if DS_MMA_WAIT == 0
+  mbar_wait(bar, parity);
+#else
+  uint32_t spins = 0;
+  while (!(DS_MMA_WAIT == 1 ? mbar_try_wait_nohint(bar, parity) : mbar_test_wait(bar, parity))) {
+    if (++spins == (1u << 28)) __trap();
+  }
+#endif
+}
+
 template <int D, bool kBf16, int MODE>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_ks,
@@ -219,11 +241,11 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     mbar_init(q_empty, 1);
     for (int h = 0; h < 2; ++h) {
       mbar_init(&s_full[h], 1);
-      mbar_init(&p_full[h], 512);
+      mbar_init(&p_full[h], DS_WARP_ARRIVE ? 16 : 512);
     }
     mbar_init(o_full, 1);
     mbar_init(pv_half, 1);
-    mbar_init(o_empty, 256);
+    mbar_init(o_empty, DS_WARP_ARRIVE ? 8 : 256);
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
@@ -322,10 +344,10 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         DS_TRACE_EV(10 + h);
         const uint32_t idesc_qk = umma_idesc_f16(fmt, kBlockQ, (uint32_t)((rows + 15) & ~15), 0, 0);
         if (h == 0 && G.first_of_stream) {
-          mbar_wait(q_full, sc & 1);
+          mma_wait(q_full, sc & 1);
           ++sc;
         }
-        mbar_wait(&kv_full[stage], phase);
+        mma_wait(&kv_full[stage], phase);
         DS_TRACE_EV(12 + h);
         tc_fence_after_sync();
         const uint64_t k_desc = k_desc0 + (uint64_t)((stage * C::STAGE_BYTES) >> 4);
@@ -346,21 +368,32 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       auto issue_pv = [&](const GroupInfo& G, int h) {
         const int rows = h ? G.rowsB : G.rowsA;
         DS_TRACE_EV(20 + h);
-        mbar_wait(&p_full[h], (h ? pv_cntB : pv_cntA) & 1);
+        mma_wait(&p_full[h], (h ? pv_cntB : pv_cntA) & 1);
         DS_TRACE_EV(22 + h);
-        if (h == 0 && G.first_of_item) mbar_wait(o_empty, (items_pv & 1) ^ 1);
-        mbar_wait(&kv_full[stage], phase);
+        if (h == 0 && G.first_of_item) mma_wait(o_empty, (items_pv & 1) ^ 1);
+        mma_wait(&kv_full[stage], phase);
         DS_TRACE_EV(24 + h);
         tc_fence_after_sync();
         const uint64_t v_desc = v_desc0 + (uint64_t)((stage * C::STAGE_BYTES) >> 4);
         const int ksteps = (rows + 15) >> 4;
-#pragma unroll 1
-        for (int ks = 0; ks < ksteps; ++ks) {
+        auto pv_step = [&](int ks) {
           // A = P[:, 16 ks .. 16 ks + 15]: 8 packed TMEM columns inside the 32-column quarter the kv columns belong to
           const uint32_t a_tmem = tmem_base + kTmemS + h * kHalfKV + (ks >> 1) * 32 + (ks & 1) * 8;
           const uint32_t acc = (G.first_of_item && h == 0 && ks == 0) ? 0u : 1u;
           umma_f16_ts(tmem_base + kTmemO, a_tmem, v_desc + (uint64_t)((ks * 16 * C::SUB_BYTES) >> 4), idesc_pv, acc);
           umma_f16_ts(tmem_base + kTmemL, a_tmem, ones_desc, idesc_l, acc);   // l += P . 1
+        };
+#if DS_PV_UNROLL
+        // full halves (the common case) with compile-time operand offsets: the rolled loop spends ~25 dependent
+        // uniform-datapath instructions per step, about as long as the tensor core needs for the step itself
+        if (ksteps == kHalfKV / 16) {
+#pragma unroll
+          for (int ks = 0; ks < kHalfKV / 16; ++ks) pv_step(ks);
+        } else
+#endif
+        {
+#pragma unroll 1
+          for (int ks = 0; ks < ksteps; ++ks) pv_step(ks);
         }
         umma_commit(&kv_empty[stage]);
         advance();
@@ -417,9 +450,17 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         uint32_t v[32];
         tmem_ld_x32(s_col + h * kHalfKV, v);   // also when nv == 0: stale columns, never used
         tmem_wait_ld();
+        // ragged tail (rare): columns past the kv length hold stale data, possibly NaN -- overwrite them with -inf once,
+        // so that the common path below carries no per-column selects (-inf is neutral for the maximum and
+        // exp2(-inf * scale - m) = 0; the host guarantees scale > 0)
+        if (nv < 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j >= nv) v[j] = 0xff800000u;
+        }
         // ---- row maximum of this half (4 threads per row exchange through shared memory)
         float m;
-        if (nv == 32) {
+        {
           float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
@@ -429,11 +470,6 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             a3 = fmaxf(a3, fmaxf(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])));
           }
           m = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
-        } else {
-          m = -INFINITY;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nv) m = fmaxf(m, __uint_as_float(v[j]));
         }
         m *= sl2;
         float* mx = sMax + (w & 1) * 512;
@@ -491,17 +527,18 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               e0 = fast_exp2(x0);
               e1 = fast_exp2(x1);
             }
-            if (nv < 32) {             // select, not multiply: stale columns may hold NaN
-              if (j >= nv) e0 = 0.f;
-              if (j + 1 >= nv) e1 = 0.f;
-            }
             pk[j >> 1] = pack2<kBf16>(e0, e1);
           }
           tmem_st_x16(s_col + h * kHalfKV, pk);
         }
         tmem_wait_st();
         tc_fence_before_sync();
+#if DS_WARP_ARRIVE
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[h]);
+#else
         mbar_arrive(&p_full[h]);
+#endif
         DS_TRACE_EV(38 + h);
         if (h) ++cntB; else ++cntA;
       }
@@ -564,7 +601,12 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           if (cross) tmem_ld_x8(os_col + (c + 1) * 8, os[cur ^ 1]);
         } else {
           tc_fence_before_sync();
+#if DS_WARP_ARRIVE
+          __syncwarp();
+          if (lane == 0) mbar_arrive(o_empty);
+#else
           mbar_arrive(o_empty);
+#endif
         }
         if constexpr (MODE == ATTN_MODE_STORE) {
           uint32_t pk[8];

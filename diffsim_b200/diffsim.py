@@ -68,6 +68,38 @@ def aas_score(A: QKV, B: QKV, similarity: str = "cosine", scale: Optional[float]
     return s if similarity == "cosine" else s.reshape(())
 
 
+def aas_score_ip_adapter(A, B, similarity: str = "cosine", scale: Optional[float] = None,
+                         match_reference_dtype: bool = True) -> torch.Tensor:
+    """The IP-Adapter ("DiffSim-C") tail of DiffSim.diffsim -- diffsim/diffsim.py:172-175,184-185.
+
+    A = (query, [ip_key_i], [ip_value_i]) as hacked_IPAdapterAttnProcessor2_0 returns them (diffsim/hacked_attn.py:
+    306-307,335): the queries of the image's latent tokens and, per loaded adapter, the keys / values of its image-
+    prompt tokens (4 for IP-Adapter, 16 for IP-Adapter-Plus).  Per adapter i the cross attention Attn(Q_A, K_B[i],
+    V_B[i]) is compared with Attn(Q_A, K_A[i], V_A[i]); the score is the mean over adapters of the flat cosines,
+    averaged over the two directions.  One fused launch per (direction, adapter): kv length = #ip tokens, which the
+    kernel handles as a ragged tail (zero-filled by TMA, masked to -inf in the softmax).
+
+    The reference's MSE branch for this path cannot run (`[...].sum()` on a Python list, diffsim/diffsim.py:191-192
+    raises AttributeError); the same error type is raised here rather than inventing semantics."""
+    (qa, ka_l, va_l), (qb, kb_l, vb_l) = A, B
+    if similarity != "cosine":
+        raise AttributeError("'list' object has no attribute 'sum' (the reference's IP-Adapter MSE branch, "
+                             "diffsim/diffsim.py:191-192, is not executable; only similarity='cosine' is defined)")
+    if not (len(ka_l) == len(va_l) == len(kb_l) == len(vb_l)) or len(ka_l) == 0:
+        raise RuntimeError("both images need the same, non-zero number of ip key/value tensors")
+    one, off = [0], [0, 1]
+    d_ab = [ops.aas_groups(qa[None], ka[None], va[None], kb[None], vb[None], one, off, one, "cosine", scale)
+            for ka, va, kb, vb in zip(ka_l, va_l, kb_l, vb_l)]
+    d_ba = [ops.aas_groups(qb[None], kb[None], vb[None], ka[None], va[None], one, off, one, "cosine", scale)
+            for ka, va, kb, vb in zip(ka_l, va_l, kb_l, vb_l)]
+    if match_reference_dtype:
+        dt = qa.dtype   # torch.mean(torch.stack([...], dim=0)) of (1,) fp16 tensors is a 0-d fp16 tensor
+        m_ab = torch.mean(torch.stack([d.to(dt) for d in d_ab], dim=0))
+        m_ba = torch.mean(torch.stack([d.to(dt) for d in d_ba], dim=0))
+        return (m_ab + m_ba) / 2
+    return (torch.stack(d_ab).mean() + torch.stack(d_ba).mean()) * 0.5
+
+
 # --------------------------------------------------------------------------------------------------------
 # trunks
 # --------------------------------------------------------------------------------------------------------
@@ -100,6 +132,17 @@ class SyntheticTrunk(Trunk):
         q, k, v = self.model.image(self._bases[concept], alpha, self.dtype, self.layout, g)
         mv = lambda t: _to_device_keep_layout(t, self.device)  # noqa: E731
         return mv(q), mv(k), mv(v)
+
+    def extract_ip(self, image, img_size=512, prompt="", target_block="up_blocks", target_layer=0, target_step=0,
+                   generator=None, ip_tokens: int = 16, n_adapters: int = 1):
+        """(query, [ip_key], [ip_value]) as the hacked IP-Adapter processor returns them (diffsim/hacked_attn.py:
+        306-307,335): latent-token queries and the keys / values of `ip_tokens` image-prompt tokens per adapter.
+        The prompt tokens are the first rows of the image's own hidden state pushed through the k / v projections --
+        like the real ones they are a function of the image only."""
+        q, k, v = self.extract(image, img_size, prompt, target_block, target_layer, target_step, generator)
+        ks = [k[:, :, i * ip_tokens:(i + 1) * ip_tokens] for i in range(n_adapters)]
+        vs = [v[:, :, i * ip_tokens:(i + 1) * ip_tokens] for i in range(n_adapters)]
+        return q, ks, vs
 
 
 def _to_device_keep_layout(t: torch.Tensor, device) -> torch.Tensor:
@@ -172,9 +215,9 @@ class DiffSim:
 
     def __init__(self, torch_dtype=torch.float16, device="cuda", ip_adapter=False, trunk: Optional[Trunk] = None,
                  match_reference_dtype: bool = True, compat_layer_collapse: bool = True):
-        if ip_adapter:
-            raise NotImplementedError("the IP-Adapter (DiffSim-C) path is not built; the reference's own hook for it "
-                                      "cannot fire (attn2 receives encoder_hidden_states as a keyword, SURVEY.md 5)")
+        # ip_adapter=True: the trunk must provide extract_ip() (query + per-adapter ip keys / values).  In the reference
+        # the hook that should capture them cannot fire (attn2 receives encoder_hidden_states as a keyword, SURVEY.md
+        # section 5); the scoring arithmetic of diffsim/diffsim.py:172-175,184-185 is implemented regardless.
         self.device, self.ip_adapter, self.torch_dtype = device, ip_adapter, torch_dtype
         self.trunk = trunk if trunk is not None else SyntheticTrunk(dtype=torch_dtype, device=device)
         self.match_reference_dtype = match_reference_dtype
@@ -184,6 +227,12 @@ class DiffSim:
                 seed="2333", device="cuda", similarity="cosine"):
         layer = resolve_sd15_layer(target_layer, self.compat_layer_collapse)
         generator = get_generator(seed, "cpu" if isinstance(self.trunk, SyntheticTrunk) else device)
+        if ip_adapter:
+            if not hasattr(self.trunk, "extract_ip"):
+                raise NotImplementedError("this trunk does not capture IP-Adapter keys / values (extract_ip)")
+            A = self.trunk.extract_ip(image_A, img_size, prompt, target_block, layer, target_step, generator)
+            B = self.trunk.extract_ip(image_B, img_size, prompt, target_block, layer, target_step, generator)
+            return aas_score_ip_adapter(A, B, similarity, None, self.match_reference_dtype)
         A = self.trunk.extract(image_A, img_size, prompt, target_block, layer, target_step, generator)
         B = self.trunk.extract(image_B, img_size, prompt, target_block, layer, target_step, generator)
         return aas_score(A, B, similarity, None, self.match_reference_dtype)
@@ -212,6 +261,11 @@ class diffsim_xl:  # noqa: N801 (the reference's name)
         B = self.trunk.extract(image_B, img_size, prompt, target_block, target_layer, target_step, generator)
         return aas_score(A, B, similarity, None, self.match_reference_dtype)
 
+    def diffsim_value(self, image_A, img_size, prompt, target_block, target_layer, target_step, seed="2333", device=None):
+        """Per-image (q,k,v) -- not in the reference's SDXL scorer; the batched drivers and caches need it."""
+        generator = get_generator(seed, "cpu" if isinstance(self.trunk, SyntheticTrunk) else self.device)
+        return self.trunk.extract(image_A, img_size, prompt, target_block, target_layer, target_step, generator)
+
 
 class diffsim_DiT:  # noqa: N801
     """DiT-XL/2 scorer -- diffsim/diffsim_dit.py:29-142.  target_layer[0] = transformer block index (0..27); the hook
@@ -229,3 +283,9 @@ class diffsim_DiT:  # noqa: N801
         A = self.trunk.extract(image_A, img_size, prompt, target_block, layer, target_step, generator)
         B = self.trunk.extract(image_B, img_size, prompt, target_block, layer, target_step, generator)
         return aas_score(A, B, similarity, None, self.match_reference_dtype)
+
+    def diffsim_value(self, image_A, img_size, prompt, target_block, target_layer, target_step, seed="2333", device=None):
+        """Per-image (q,k,v) -- not in the reference's DiT scorer; the batched drivers and caches need it."""
+        layer = target_layer[0] if not isinstance(target_layer, int) else target_layer
+        generator = get_generator(seed, "cpu" if isinstance(self.trunk, SyntheticTrunk) else self.device)
+        return self.trunk.extract(image_A, img_size, prompt, target_block, layer, target_step, generator)

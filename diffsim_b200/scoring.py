@@ -269,7 +269,8 @@ def symmetrize(dm: torch.Tensor) -> torch.Tensor:
 
 def ranked_lists(score: torch.Tensor, names: Sequence[str], topk: int = 5, larger_is_closer: bool = True,
                  skip_self: bool = True) -> List[str]:
-    """Retrieval result lines in the format retrieval_vis.py:57-68 parses: '<query>: <best> <2nd> ...'."""
+    """Compact one-line-per-query summary '<query>: <best> <2nd> ...' (for logs).  The per-query result FILES that
+    retrieval_vis.py:57-68 parses (one retrieved image per line) are written by retrieval.write_retrieval_results."""
     n = score.shape[0]
     s = score.clone().float()
     if skip_self:

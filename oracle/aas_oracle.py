@@ -216,3 +216,42 @@ def reference_capture(hidden: torch.Tensor, wq: torch.Tensor, wk: torch.Tensor, 
         y = F.linear(hidden, w)
         out.append(y.view(B, S, heads, y.shape[-1] // heads).transpose(1, 2))
     return tuple(out)
+
+
+# ----------------------------------------------------------------------------------------------------
+# baseline-metric AAS variants
+# ----------------------------------------------------------------------------------------------------
+def clip_attention_calc(q, k, v, scale: float, hidden_size_shape, out_w: torch.Tensor, out_b: Optional[torch.Tensor],
+                        round_to: Optional[torch.dtype] = None) -> torch.Tensor:
+    """metrics/clip_i.py:113-127: attention with an explicit scale, heads merged to (bsz, tgt_len, embed_dim), out_proj.
+    round_to models the 16-bit storage of the attention output and of the projection result."""
+    bsz, tgt_len, embed_dim = hidden_size_shape
+    o = attention(q, k, v, scale, round_to=round_to)
+    o = o.transpose(1, 2).reshape(bsz, tgt_len, embed_dim)
+    y = torch.matmul(o, out_w.to(torch.float64).t())
+    if out_b is not None:
+        y = y + out_b.to(torch.float64)
+    if round_to is not None:
+        y = y.to(round_to).to(torch.float64)
+    return y
+
+
+def clip_cross_score(qa, ka, va, qb, kb, vb, scale: float, hidden_size_shape, out_w, out_b,
+                     round_to: Optional[torch.dtype] = None) -> float:
+    """metrics/clip_i.py:130-159."""
+    f = lambda q, k, v: clip_attention_calc(q, k, v, scale, hidden_size_shape, out_w, out_b, round_to)  # noqa: E731
+    a_on_b, b_on_a, self_a, self_b = f(qa, kb, vb), f(qb, ka, va), f(qa, ka, va), f(qb, kb, vb)
+    return (flat_cosine(a_on_b, self_a) + flat_cosine(b_on_a, self_b)) / 2.0
+
+
+def gram_matrix(features: torch.Tensor, round_to: Optional[torch.dtype] = None) -> torch.Tensor:
+    """metrics/vgg_gram.py:57-69: (b,d,h,w) -> (b*d, h*w) -> F F^T."""
+    b, d, h, w = features.shape
+    f = features.reshape(b * d, h * w).to(torch.float64)
+    g = f @ f.t()
+    return g.to(round_to).to(torch.float64) if round_to is not None else g
+
+
+def gram_similarity(fa: torch.Tensor, fb: torch.Tensor, round_to: Optional[torch.dtype] = None) -> float:
+    """metrics/vgg_gram.py:81: cosine of the last ROW of each Gram matrix (as written in the reference)."""
+    return flat_cosine(gram_matrix(fa, round_to)[-1], gram_matrix(fb, round_to)[-1])

@@ -8,6 +8,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN_PATH = os.path.join(ROOT, "tests", "golden", "aas_golden.pt")
+METRICS_GOLDEN_PATH = os.path.join(ROOT, "tests", "golden", "metrics_golden.pt")
 
 
 def pytest_configure(config):
@@ -19,6 +20,43 @@ def golden():
     import torch
 
     return torch.load(GOLDEN_PATH, weights_only=False)
+
+
+@pytest.fixture(scope="session")
+def metrics_golden():
+    import torch
+
+    return torch.load(METRICS_GOLDEN_PATH, weights_only=False)
+
+
+def ip_images(seed, ip_tokens, n_adapters, alpha):
+    """The inputs of an IP-Adapter golden case (same recipe as tests/golden/make_golden_metrics.py:ip_images)."""
+    import torch
+
+    from diffsim_b200 import synth
+
+    m = synth.SynthModel(2, 8, 256, 160, seed=2334)
+    g = torch.Generator().manual_seed(seed)
+    base = m.new_base(g)
+    imgs = []
+    for a in (1.0, alpha):
+        q, k, v = m.image(base, a, torch.float16, "sd", g)
+        ks = [k[:, :, i * ip_tokens:(i + 1) * ip_tokens] for i in range(n_adapters)]
+        vs = [v[:, :, i * ip_tokens:(i + 1) * ip_tokens] for i in range(n_adapters)]
+        imgs.append((q, ks, vs))
+    return imgs
+
+
+def dino_images():
+    """The inputs of the dino_cross golden case (tests/golden/make_golden_metrics.py:dino_images)."""
+    import torch
+
+    from diffsim_b200 import synth
+
+    g = torch.Generator().manual_seed(33)
+    md = synth.SynthModel(1, 6, 257, 64, seed=78)
+    based = md.new_base(g)
+    return md.image(based, 1.0, torch.float16, "sd", g), md.image(based, 0.6, torch.float16, "sd", g)
 
 
 def regenerate_case(case):

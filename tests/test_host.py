@@ -41,14 +41,14 @@ def test_row_blocks_cover_everything_once():
         assert max(sizes) - min(sizes) <= 1
 
 
-def test_ranked_lists_format_is_what_retrieval_vis_parses():
+def test_ranked_lists_summary_lines():
     names = [f"{c}_{i}" for c in ("cat", "dog") for i in range(3)]
     S = torch.eye(6) * 0 + torch.tensor([[1 if a // 3 == b // 3 else 0 for b in range(6)] for a in range(6)]).float()
     S = S + 0.01 * torch.arange(6).float()[None]
     lines = scoring.ranked_lists(S, names, topk=2)
     assert len(lines) == 6
     for ln, name in zip(lines, names):
-        head, rest = ln.split(":")            # retrieval_vis.py:57-68: first token '<cls>_<id>:', best first
+        head, rest = ln.split(":")            # '<query>: <best> <2nd>' (the parser-format files: tests/test_metrics_cpu.py)
         assert head == name and len(rest.split()) == 2
         assert all(r.split("_")[0] == name.split("_")[0] for r in rest.split())
         assert name not in rest.split()

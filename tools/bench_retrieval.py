@@ -1,0 +1,165 @@
+#!/usr/bin/env python
+"""All-pairs retrieval benchmark (BASELINE.json configs[2]: Sref-shaped, N = 2032 images, SD-1.5 up_blocks L0 shape):
+the directional N x N AAS matrix, row-block sharded over the ranks, K and V exchanged with NCCL all_gather.
+
+    python tools/bench_retrieval.py --images 2032                                           # 1 GPU
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/bench_retrieval.py --images 2032                                              # row-block sharded
+
+Every rank generates its own row block of images on its device (508 "styles" x 4 images; a style's images share a
+base), so ground-truth neighbours exist and retrieval precision is reported.  Timed on the device with CUDA events,
+max over ranks: (a) the K/V all-gather, (b) the local block of the matrix (one ds_aas_matrix call), (c) the gather of
+the row blocks.  Strong scaling: the total work is fixed.  Prints one JSON line on rank 0; with --check, the 1-rank
+matrix of the same images is recomputed on rank 0 and compared bitwise with the gathered one.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def style_images(B, H, S, D, i0, i1, per_style, dtype, device, alpha=0.8, seed=2334):
+    """Images [i0, i1) of the style set: image i belongs to style i // per_style.  Deterministic per image (the
+    generator is re-seeded per style / image), so any rank can build any image."""
+    import torch
+
+    C = H * D
+    g = torch.Generator(device=device).manual_seed(seed)
+    std = 1.0 / math.sqrt(C)
+    Wq = torch.randn(C, C, generator=g, device=device) * (std * 2.2)
+    Wk = torch.randn(C, C, generator=g, device=device) * (std * 2.2)
+    Wv = torch.randn(C, C, generator=g, device=device) * std
+    mems = [torch.empty(i1 - i0, B, S, C, dtype=dtype, device=device) for _ in range(3)]
+    for i in range(i0, i1):
+        gs = torch.Generator(device=device).manual_seed(1000003 + i // per_style)
+        base = torch.randn(1, S, C, generator=gs, device=device).repeat(B, 1, 1)
+        if B > 1:
+            base[1:] += 0.1 * torch.randn(B - 1, S, C, generator=gs, device=device)
+        gi = torch.Generator(device=device).manual_seed(7000001 + i)
+        h = alpha * base + math.sqrt(1 - alpha * alpha) * torch.randn(B, S, C, generator=gi, device=device)
+        mems[0][i - i0] = (h @ Wq).to(dtype)
+        mems[1][i - i0] = (h @ Wk).to(dtype)
+        mems[2][i - i0] = (h @ Wv).to(dtype)
+    return tuple(m.view(i1 - i0, B, S, H, D).permute(0, 1, 3, 2, 4) for m in mems)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--images", type=int, default=2032)
+    ap.add_argument("--per-style", type=int, default=4)
+    ap.add_argument("--shape", type=int, nargs=4, default=[2, 8, 256, 160])
+    ap.add_argument("--dtype", default="f16", choices=["f16", "bf16"])
+    ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--check", action="store_true", help="rank 0 recomputes the unsharded matrix and compares bitwise")
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+
+    import torch
+    import torch.distributed as dist
+
+    from diffsim_b200 import ops, retrieval, scoring
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.float16 if args.dtype == "f16" else torch.bfloat16
+    B, H, S, D = args.shape
+    N = args.images
+    r0, r1 = scoring.row_block(N, rank, world)
+    cache = scoring.QKVCache(*style_images(B, H, S, D, r0, r1, args.per_style, dtype, dev))
+    torch.cuda.synchronize()
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        if world > 1:
+            _, km, vm = cache.memory()
+            counts = [scoring.row_block(N, r, world) for r in range(world)]
+            nmax = max(b - a for a, b in counts)
+
+            def gather(mem):
+                pad = mem if mem.shape[0] == nmax else torch.cat([mem, mem.new_zeros((nmax - mem.shape[0],) + tuple(mem.shape[1:]))], 0)
+                out = torch.empty((world * nmax,) + tuple(mem.shape[1:]), dtype=mem.dtype, device=dev)
+                dist.all_gather_into_tensor(out, pad.contiguous())
+                if all(b - a == nmax for a, b in counts):
+                    return out
+                return torch.cat([out[r * nmax: r * nmax + (b - a)] for r, (a, b) in enumerate(counts)], 0)
+
+            k_all, v_all = gather(km), gather(vm)
+            view = lambda m: m.view(m.shape[0], B, S, H, D).permute(0, 1, 3, 2, 4)  # noqa: E731
+            k_all, v_all = view(k_all), view(v_all)
+        else:
+            k_all, v_all = cache.k, cache.v
+        ev[1].record()
+        block = ops.aas_matrix(cache.q, cache.k, cache.v, k_all, v_all, "cosine")
+        ev[2].record()
+        if world > 1:
+            counts = [scoring.row_block(N, r, world) for r in range(world)]
+            nmax = max(b - a for a, b in counts)
+            pad = block if block.shape[0] == nmax else torch.cat([block, block.new_zeros((nmax - block.shape[0], N))], 0)
+            out = torch.empty((world * nmax, N), dtype=block.dtype, device=dev)
+            dist.all_gather_into_tensor(out, pad.contiguous())
+            dm = torch.cat([out[r * nmax: r * nmax + (b - a)] for r, (a, b) in enumerate(counts)], 0)
+        else:
+            dm = block
+        ev[3].record()
+        torch.cuda.synchronize()
+        t = torch.tensor([ev[i].elapsed_time(ev[i + 1]) for i in range(3)] + [ev[0].elapsed_time(ev[3])], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return dm, t.tolist()
+
+    sync()
+    dm, _ = step()          # warm-up (NCCL communicator, tensor maps)
+    best = None
+    for _ in range(args.reps):
+        sync()
+        dm, t = step()
+        if best is None or t[3] < best[3]:
+            best = t
+    ms_gather, ms_matrix, ms_collect, ms_total = best
+    flops = (N * N + N) * 4.0 * B * H * S * S * D   # N^2 cross attentions (incl. the diagonal) + N self attentions
+    kv_bytes = 2 * N * B * H * S * D * 2
+    res = {"workload": "sref_all_pairs_sd15_512_up0_cosine", "images": N, "shape_BHSD": [B, H, S, D], "dtype": args.dtype,
+           "n_gpus": world, "scaling": "strong", "ms_total": ms_total, "ms_allgather_kv": ms_gather, "ms_matrix": ms_matrix,
+           "ms_gather_rows": ms_collect, "scores_per_sec": N * N / (ms_total * 1e-3),
+           "pairs_per_sec": N * (N - 1) / 2 / (ms_total * 1e-3),
+           "attn_tflops_whole_job": flops / (ms_matrix * 1e-3) / 1e12,
+           "allgather_recv_GBps_per_rank": (world - 1) / world * kv_bytes / (ms_gather * 1e-3) / 1e9 if world > 1 else None,
+           "timing": "CUDA events on the launching stream, max over ranks, best of %d after one warm-up" % args.reps}
+    if rank == 0:
+        s = scoring.symmetrize(dm)
+        labels = [i // args.per_style for i in range(N)]
+        res["retrieval"] = retrieval.retrieval_accuracy(s, labels, topk=args.per_style - 1)
+        if args.check and world > 1:
+            full = scoring.QKVCache(*style_images(B, H, S, D, 0, N, args.per_style, dtype, dev))
+            ref = ops.aas_matrix(full.q, full.k, full.v, full.k, full.v, "cosine")
+            res["bitwise_equal_to_single_gpu"] = bool(torch.equal(ref, dm))
+            res["max_abs_diff_to_single_gpu"] = float((ref - dm).abs().max())
+        line = json.dumps(res)
+        print(line)
+        if args.out:
+            os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
+            with open(args.out, "w") as f:
+                f.write(line + "\n")
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
