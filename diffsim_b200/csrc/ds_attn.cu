@@ -61,7 +61,7 @@ constexpr int kTmemS = 0;        // S_A: columns [0,128), S_B: [128,256); P of t
 constexpr int kTmemO = 256;      // O: [256, 256 + D_PAD)
 constexpr int kTmemOs = 416;     // O_self, packed 16-bit: [416, 416 + D_PAD/2)
 #ifndef DS_PV_UNROLL
-#define DS_PV_UNROLL 0
+#define DS_PV_UNROLL 1
 #endif
 #ifndef DS_WARP_ARRIVE
 #define DS_WARP_ARRIVE 0     // 1: one elected lane per warp arrives on p_full / o_empty (16 / 8 arrivals instead of 512 / 256)

@@ -217,44 +217,76 @@ def aas_matrix_local(rows: QKVCache, cols: QKVCache, similarity: str = "cosine",
 
 
 def aas_matrix_sharded(local: QKVCache, similarity: str = "cosine", scale: Optional[float] = None, group=None,
-                       gather_to_all: bool = True) -> torch.Tensor:
+                       gather_to_all: bool = True, timings: Optional[dict] = None) -> torch.Tensor:
     """All-pairs directional matrix with the images row-block sharded over the ranks of `group`.
 
     Each rank holds the Q/K/V of its own images.  K and V are exchanged with one all_gather each (NCCL over
-    NVLink on GPUs, gloo on CPU tests); Q and the self attention stay local; every rank computes
+    NVLink on GPUs, gloo on CPU tests), issued asynchronously: while they are in flight the rank already scores its
+    rows against its OWN columns; the columns of every peer follow, one kernel call per peer, reading the gathered
+    buffer in place (no concatenation copy).  Q and the self attention stay local.  Every rank computes
     Dm[own rows, :] and the row blocks are gathered at the end.  Per-element arithmetic does not depend on the
-    sharding, so the result is bit-identical to the single-device matrix.
+    sharding or on how the columns are cut into calls, so the result is bit-identical to the single-device matrix.
+    `timings` (optional dict) receives CUDA events: 'start', 'own_done', 'exchange_done', 'block_done', 'end'.
     """
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
     _, km, vm = local.memory()
-    n_local = torch.tensor([km.shape[0]], dtype=torch.int64, device=km.device)
+    dev = km.device
+    B, H, S, D = local.shape
+    n_local = torch.tensor([km.shape[0]], dtype=torch.int64, device=dev)
     counts = [torch.zeros_like(n_local) for _ in range(world)]
     dist.all_gather(counts, n_local, group=group)
     counts = [int(c) for c in counts]
-    nmax = max(counts)
+    nmax, n_total = max(counts), sum(counts)
+    offs = [sum(counts[:r]) for r in range(world)]
 
-    def gather(mem):
-        pad = mem
-        if mem.shape[0] < nmax:
-            pad = torch.cat([mem, mem.new_zeros((nmax - mem.shape[0],) + tuple(mem.shape[1:]))], 0)
-        outs = [torch.empty_like(pad) for _ in range(world)]
-        dist.all_gather(outs, pad.contiguous(), group=group)
-        return torch.cat([o[:c] for o, c in zip(outs, counts)], 0)
+    def mark(name):
+        if timings is not None and dev.type == "cuda":
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            timings[name] = ev
 
-    k_all, v_all = gather(km), gather(vm)
-    n, B, H, S, D = (k_all.shape[0],) + tuple(local.shape)
+    def padded(mem):
+        if mem.shape[0] == nmax:
+            return mem.contiguous()
+        return torch.cat([mem, mem.new_zeros((nmax - mem.shape[0],) + tuple(mem.shape[1:]))], 0)
+
+    mark("start")
+    k_all = torch.empty((world, nmax, B, S, H * D), dtype=km.dtype, device=dev)
+    v_all = torch.empty_like(k_all)
+    pending = []
+    if nmax > 0:
+        pending = [dist.all_gather_into_tensor(k_all.view(world * nmax, B, S, H * D), padded(km), group=group, async_op=True),
+                   dist.all_gather_into_tensor(v_all.view(world * nmax, B, S, H * D), padded(vm), group=group, async_op=True)]
+    block = torch.zeros((counts[rank], n_total), dtype=torch.float32 if dev.type == "cuda" else torch.float64, device=dev)
+    if counts[rank] > 0:
+        # own columns first: this work hides the exchange
+        block[:, offs[rank]: offs[rank] + counts[rank]] = _matrix_block(local, local.k, local.v, similarity, scale)
+    mark("own_done")
+    for w in pending:
+        w.wait()
+    mark("exchange_done")
     view = lambda m: m.view(m.shape[0], B, S, H, D).permute(0, 1, 3, 2, 4)  # noqa: E731
-    block = _matrix_block(local, view(k_all), view(v_all), similarity, scale)
+    if counts[rank] > 0:
+        for p in range(world):
+            if p == rank or counts[p] == 0:
+                continue
+            block[:, offs[p]: offs[p] + counts[p]] = _matrix_block(local, view(k_all[p, : counts[p]]),
+                                                                  view(v_all[p, : counts[p]]), similarity, scale)
+    mark("block_done")
     if not gather_to_all:
+        mark("end")
         return block
     pad = block
     if block.shape[0] < nmax:
         pad = torch.cat([block, block.new_zeros((nmax - block.shape[0], block.shape[1]))], 0)
-    outs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(outs, pad.contiguous(), group=group)
-    return torch.cat([o[:c] for o, c in zip(outs, counts)], 0)
+    out = torch.empty((world * nmax, n_total), dtype=block.dtype, device=dev)
+    if nmax > 0:
+        dist.all_gather_into_tensor(out, pad.contiguous(), group=group)
+    mark("end")
+    return torch.cat([out[r * nmax: r * nmax + c] for r, c in enumerate(counts)], 0)
 
 
 def _matrix_block(local: QKVCache, k_all: torch.Tensor, v_all: torch.Tensor, similarity, scale):
