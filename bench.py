@@ -221,6 +221,8 @@ def main():
     ap.add_argument("--dtype", default="float16", choices=["float16", "bfloat16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the K2 / K3 secondary roofline measurements")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: do not bind ranks to their GPU's NUMA-local CPUs")
     ap.add_argument("--profiler-range", action="store_true",
                     help="bracket the timed device-resident steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -240,6 +242,9 @@ def main():
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # pinned staging buffers of the end-to-end leg should be local to the GPU's socket: bind before allocating them
+    from diffsim_b200 import hostbind
+    numa = hostbind.bind_to_gpu_node(local_rank) if world > 1 and not args.no_numa_bind else {"bound": False, "why": "single rank"}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -390,6 +395,61 @@ def main():
                                      "correct": c_q[0]}
         del host, scorer, hscorer, hid_host
 
+    # ---- secondary kernels (rank 0): K2 reductions vs HBM, K3 similarity GEMM vs tensor peak ----------------------
+    if rank == 0 and not args.no_secondary:
+        torch.cuda.empty_cache()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        E = B * H * S * D
+        P2 = 256                                  # 2 x 256 x 1.31 MB = 671 MB of inputs: larger than the 126 MB L2
+        g = torch.Generator(device=dev).manual_seed(7)
+        x = torch.randn(P2, E, generator=g, device=dev, dtype=torch.float32).to(dtype)
+        y = (0.6 * x.float() + 0.4 * torch.randn(P2, E, generator=g, device=dev)).to(dtype)
+        for mode in ("cosine", "minmax_cosine"):
+            for _ in range(3):
+                ops.pair_reduce(x, y, mode)
+            e0.record()
+            for _ in range(10):
+                ops.pair_reduce(x, y, mode)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms2 = e0.elapsed_time(e1) / 10
+            by = 2.0 * P2 * E * x.element_size() + 4 * P2
+            extra["roofline_k2" if mode == "cosine" else "roofline_k2_minmax"] = {
+                "kernel": f"pair_reduce_kernel<{args.dtype},{mode}> (batched flat reduction, one pass)", "bound": "hbm",
+                "achieved": by / (ms2 * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": by / (ms2 * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "bytes_per_launch": by,
+                "ms_per_launch": ms2, "pairs_per_launch": P2,
+                "algorithmic": "2 * E * sizeof(dtype) read + 4 B written per row pair (DESIGN.md section 3)"}
+        del x, y
+        Nf, Lf = 2032, E                          # Sref-shaped: 2032 images x flattened (2,256,1280) diffeats features
+        feats = torch.empty(Nf, Lf, dtype=dtype, device=dev)
+        for i0 in range(0, Nf, 127):
+            feats[i0:i0 + 127] = torch.randn(min(127, Nf - i0), Lf, generator=g, device=dev).to(dtype)
+        outm = torch.empty(Nf, Nf, dtype=torch.float32, device=dev)
+        for _ in range(2):
+            ops.simmat(feats, None, "cosine", out=outm)
+        e0.record()
+        for _ in range(3):
+            ops.simmat(feats, None, "cosine", out=outm)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms3 = e0.elapsed_time(e1) / 3
+        # self-similarity runs the upper-triangle tile schedule: EXECUTED flops = tiles on/above the diagonal x 128 x 256 x 2L
+        tm_n, tn_n = (Nf + 127) // 128, (Nf + 255) // 256
+        tiles_exec = sum(max(0, tn_n - (tm * 128) // 256) for tm in range(tm_n))
+        fl3 = 2.0 * tiles_exec * 128 * 256 * Lf
+        extra["roofline_k3"] = {"kernel": "simmat: row statistics + gemm_tn_kernel<EPI_F32> (upper-triangle tiles, split-K) + "
+                                          "normalise/mirror (N x N cosine)",
+                                "bound": "tensor", "achieved": fl3 / (ms3 * 1e-3) / 1e12, "peak": peaks["bf16_tflops"],
+                                "unit": "TFLOP/s", "frac": fl3 / (ms3 * 1e-3) / 1e12 / peaks["bf16_tflops"], "traffic": None,
+                                "flops_per_launch": fl3, "flops_full_matrix": 2.0 * Nf * Nf * Lf, "ms_per_call": ms3,
+                                "images": Nf, "feature_len": Lf,
+                                "full_matrix_equivalent_tflops": 2.0 * Nf * Nf * Lf / (ms3 * 1e-3) / 1e12,
+                                "note": "whole ds_simmat call (one statistics pass + GEMM + finish); achieved counts the flops "
+                                        "EXECUTED (72 of 128 tiles), full_matrix_equivalent the 2*N*N*L of the result",
+                                "diag_minus_one_max": float((outm.diagonal() - 1).abs().max())}
+        del feats, outm
+
     # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -413,7 +473,7 @@ def main():
                                          "boundary: H2D of hidden states + K4 projection",
                        "l2": f"inputs {resident_gib:.1f} GiB per step > 126 MB L2 (no flush needed)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-            "clocks": sampler.summary(), "correct_2afc": correct,
+            "clocks": sampler.summary(), "correct_2afc": correct, "numa_bind": numa,
         }
         line.update(extra)
         print(json.dumps(line))

@@ -36,6 +36,8 @@ struct GemmParams {
   int tiles_m, tiles_n;
   int kb_total;             // 64-wide k blocks
   int splits, kb_per_split;
+  int sym;                  // 1: C is symmetric (B == A): only tiles holding an element with row <= col are computed
+  int tiles_used;           // tiles per split (tiles_m * tiles_n, or the upper-triangle count when sym)
   uint32_t idesc;
   // GEMM_EPI_F32: part[split][M][N] fp32
   float* part;
@@ -47,6 +49,38 @@ struct GemmParams {
   int cols_per_out;
   const void* bias;
 };
+
+// tiles of one split, n fastest.  Symmetric mode enumerates, row of tiles by row of tiles, only the tiles that hold an
+// element on or above the diagonal: tile (tm, tn) is needed iff tm * kGBM <= tn * kGBN + kGBN - 1, i.e. tn >= tm*kGBM / kGBN.
+__host__ __device__ __forceinline__ int gemm_sym_first_tn(int tm) { return (tm * kGBM) / kGBN; }
+
+__device__ __forceinline__ void gemm_decode_tile(const GemmParams& p, int tile, int& tm, int& tn) {
+  if (!p.sym) {
+    tm = tile / p.tiles_n;
+    tn = tile - tm * p.tiles_n;
+    return;
+  }
+  tm = 0;
+  for (;;) {
+    const int first = gemm_sym_first_tn(tm);
+    const int cnt = p.tiles_n - first;
+    if (tile < cnt) {
+      tn = first + tile;
+      return;
+    }
+    tile -= cnt;
+    ++tm;
+  }
+}
+
+static int gemm_sym_tile_count(int tiles_m, int tiles_n) {
+  int n = 0;
+  for (int tm = 0; tm < tiles_m; ++tm) {
+    const int cnt = tiles_n - gemm_sym_first_tn(tm);
+    if (cnt > 0) n += cnt;
+  }
+  return n;
+}
 
 template <int EPI, bool kBf16>
 __global__ void __launch_bounds__(kGThreads, 1)
@@ -85,7 +119,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles = p.tiles_m * p.tiles_n;
+  const int tiles = p.tiles_used;
   const int n_units = tiles * p.splits;
 
   if (warp == 0) {
@@ -94,7 +128,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t phase = 0;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
         const int split = u / tiles, tile = u - split * tiles;
-        const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+        int tm, tn;
+        gemm_decode_tile(p, tile, tm, tn);
         const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
@@ -146,7 +181,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint32_t n_local = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++n_local) {
       const int split = u / tiles, tile = u - split * tiles;
-      const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+      int tm, tn;
+      gemm_decode_tile(p, tile, tm, tn);
       const uint32_t buf = n_local & 1u;
       mbar_wait(&acc_full[buf], (n_local >> 1) & 1u);
       tc_fence_after_sync();
@@ -235,7 +271,9 @@ static int launch_gemm_tn(const void* a, int64_t M, int64_t lda, const void* b, 
   p.kb_per_split = (p.kb_total + p.splits - 1) / p.splits;
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   p.idesc = umma_idesc_f16(dtype == DS_BF16 ? 1u : 0u, kGBM, kGBN, 0, 0);
-  const int64_t units = (int64_t)p.tiles_m * p.tiles_n * p.splits;
+  if (p.sym && (M != N || a != b || lda != ldb)) return fail(DS_ERR_INVALID, "gemm: symmetric mode needs B == A");
+  p.tiles_used = p.sym ? gemm_sym_tile_count(p.tiles_m, p.tiles_n) : p.tiles_m * p.tiles_n;
+  const int64_t units = (int64_t)p.tiles_used * p.splits;
   if (units <= 0) return DS_OK;
   if (units > INT32_MAX) return fail(DS_ERR_INVALID, "gemm: too many work units");
   int grid = sm_count();

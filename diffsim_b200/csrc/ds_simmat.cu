@@ -112,28 +112,33 @@ __global__ void row_stats_finish_kernel(const float* __restrict__ partials, int 
 __global__ void simmat_finish_kernel(const float* __restrict__ part, int splits, int64_t part_split_stride,
                                      int64_t n_rows, int64_t n_cols, const double* __restrict__ rstats,
                                      const double* __restrict__ cstats, double L, int mode, float* __restrict__ C,
-                                     int64_t ldc) {
+                                     int64_t ldc, int sym) {
   const int64_t col_blocks = (n_cols + blockDim.x - 1) / blockDim.x;
   const int64_t r = blockIdx.x / col_blocks;
   const int64_t c = (blockIdx.x % col_blocks) * (int64_t)blockDim.x + threadIdx.x;
   if (c >= n_cols || r >= n_rows) return;
-  float acc = 0.f;
-  for (int z = 0; z < splits; ++z) acc += part[(size_t)z * part_split_stride + (size_t)r * n_cols + c];
+  // symmetric mode: only the tiles on / above the diagonal hold partials.  The thread of (r, c), c >= r, reads them
+  // (coalesced along c) and writes both C[r][c] and its mirror image; the threads below the diagonal have nothing to do
+  if (sym && c < r) return;
+  double acc = 0.0;
+  const size_t e = (size_t)r * n_cols + c;
+  for (int z = 0; z < splits; ++z) acc += (double)part[(size_t)z * part_split_stride + e];
   const double* rs = rstats + r * 4;
   const double* cs = cstats + c * 4;
   double out;
   if (mode == DS_SIM_COSINE) {
     double nx = fmax(sqrt(rs[1]), 1e-8), ny = fmax(sqrt(cs[1]), 1e-8);
-    out = (double)acc / (nx * ny);
+    out = acc / (nx * ny);
   } else {
     double ax = rs[2], cx = rs[3] - rs[2], ay = cs[2], cy = cs[3] - cs[2];
-    double dot = ((double)acc - ay * rs[0] - ax * cs[0] + L * ax * ay) / (cx * cy);
+    double dot = (acc - ay * rs[0] - ax * cs[0] + L * ax * ay) / (cx * cy);
     double xx = (rs[1] - 2.0 * ax * rs[0] + L * ax * ax) / (cx * cx);
     double yy = (cs[1] - 2.0 * ay * cs[0] + L * ay * ay) / (cy * cy);
     double nx = fmax(sqrt(fmax(xx, 0.0)), 1e-8), ny = fmax(sqrt(fmax(yy, 0.0)), 1e-8);
     out = dot / (nx * ny);
   }
   C[(size_t)r * ldc + c] = (float)out;
+  if (sym && c != r) C[(size_t)c * ldc + r] = (float)out;
 }
 
 struct SimmatPlan {
@@ -142,22 +147,29 @@ struct SimmatPlan {
   int64_t stat_chunk_elems;
 };
 
-static SimmatPlan simmat_plan(int64_t n_rows, int64_t n_cols, int64_t L) {
+static SimmatPlan simmat_plan(int64_t n_rows, int64_t n_cols, int64_t L, bool sym = false) {
   SimmatPlan p;
   p.tiles_m = (int)((n_rows + kGBM - 1) / kGBM);
   p.tiles_n = (int)((n_cols + kGBN - 1) / kGBN);
   p.kb_total = (int)((L + kGBK - 1) / kGBK);
   // split along L: the smallest split count whose work units (tiles x splits) fill whole waves of the persistent grid
   // to >= 95% (at least 8 k blocks per unit, at most 64 splits: the fp32 partials cost HBM traffic)
-  const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
+  const int64_t tiles = sym ? gemm_sym_tile_count(p.tiles_m, p.tiles_n) : (int64_t)p.tiles_m * p.tiles_n;
   int sms = sm_count();
   if (sms <= 0) sms = 148;
+  // accuracy: the tensor core adds each K = 16 MMA into the fp32 accumulator with truncation, a bias that grows with the
+  // length of the chain (measured on 655 360-long unit-cosine rows: 2.1e-3 at 20 480 MMAs per partial, 5e-4 at 1 100);
+  // a partial therefore never covers more than kMaxKbPerSplit k blocks (1024 MMAs); the partials are added in double
+  constexpr int kMaxKbPerSplit = 256;
+  const int min_s = (p.kb_total + kMaxKbPerSplit - 1) / kMaxKbPerSplit;
   int max_s = p.kb_total / 8;
   if (max_s > 64) max_s = 64;
+  if (max_s < min_s + 8) max_s = min_s + 8;
+  if (max_s > p.kb_total) max_s = p.kb_total;
   if (max_s < 1) max_s = 1;
-  int best_s = 1;
+  int best_s = min_s;
   double best_eff = 0.0;
-  for (int s = 1; s <= max_s; ++s) {
+  for (int s = min_s; s <= max_s; ++s) {
     const int kps = (p.kb_total + s - 1) / s;
     const int real_s = (p.kb_total + kps - 1) / kps;
     const int64_t units = tiles * real_s;
@@ -190,6 +202,10 @@ size_t ds_simmat_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t L) {
   using namespace ds;
   if (n_rows <= 0 || n_cols <= 0 || L <= 0) return 256;
   SimmatPlan p = simmat_plan(n_rows, n_cols, L);
+  if (n_rows == n_cols) {   // the self-similarity call may take the symmetric plan: size for the larger of the two
+    SimmatPlan ps = simmat_plan(n_rows, n_cols, L, true);
+    if (ps.splits > p.splits) p.splits = ps.splits;
+  }
   size_t b = 0;
   b += align_up((size_t)p.splits * n_rows * n_cols * sizeof(float), 256);
   b += align_up((size_t)(n_rows + n_cols) * p.stat_chunks * 4 * sizeof(float), 256);
@@ -213,7 +229,9 @@ int ds_simmat(const void* rows, int64_t n_rows, int64_t ld_rows, const void* col
   int rc = ds_device_ok();
   if (rc != DS_OK) return rc;
 
-  SimmatPlan p = simmat_plan(n_rows, n_cols, L);
+  // self-similarity (the retrieval case): C is symmetric -- compute the upper triangle of tiles only, one statistics pass
+  const bool sym = rows == cols && n_rows == n_cols && ld_rows == ld_cols;
+  SimmatPlan p = simmat_plan(n_rows, n_cols, L, sym);
   Workspace w(ws, ws_bytes);
   float* part = static_cast<float*>(w.take((size_t)p.splits * n_rows * n_cols * sizeof(float)));
   float* spart = static_cast<float*>(w.take((size_t)(n_rows + n_cols) * p.stat_chunks * 4 * sizeof(float)));
@@ -225,26 +243,29 @@ int ds_simmat(const void* rows, int64_t n_rows, int64_t ld_rows, const void* col
 
   // statistics pass
   float* spart_c = spart + (size_t)n_rows * p.stat_chunks * 4;
-  double* stats_c = stats + (size_t)n_rows * 4;
+  double* stats_c = sym ? stats : stats + (size_t)n_rows * 4;
   if (dtype == DS_F16) {
     row_stats_kernel<__half><<<(unsigned)(n_rows * p.stat_chunks), kStatThreads, 0, st>>>(
         static_cast<const __half*>(rows), ld_rows, L, p.stat_chunks, p.stat_chunk_elems, spart);
-    row_stats_kernel<__half><<<(unsigned)(n_cols * p.stat_chunks), kStatThreads, 0, st>>>(
-        static_cast<const __half*>(cols), ld_cols, L, p.stat_chunks, p.stat_chunk_elems, spart_c);
+    if (!sym)
+      row_stats_kernel<__half><<<(unsigned)(n_cols * p.stat_chunks), kStatThreads, 0, st>>>(
+          static_cast<const __half*>(cols), ld_cols, L, p.stat_chunks, p.stat_chunk_elems, spart_c);
   } else {
     row_stats_kernel<__nv_bfloat16><<<(unsigned)(n_rows * p.stat_chunks), kStatThreads, 0, st>>>(
         static_cast<const __nv_bfloat16*>(rows), ld_rows, L, p.stat_chunks, p.stat_chunk_elems, spart);
-    row_stats_kernel<__nv_bfloat16><<<(unsigned)(n_cols * p.stat_chunks), kStatThreads, 0, st>>>(
-        static_cast<const __nv_bfloat16*>(cols), ld_cols, L, p.stat_chunks, p.stat_chunk_elems, spart_c);
+    if (!sym)
+      row_stats_kernel<__nv_bfloat16><<<(unsigned)(n_cols * p.stat_chunks), kStatThreads, 0, st>>>(
+          static_cast<const __nv_bfloat16*>(cols), ld_cols, L, p.stat_chunks, p.stat_chunk_elems, spart_c);
   }
   DS_CUDA_TRY(cudaGetLastError());
   row_stats_finish_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, st>>>(spart, p.stat_chunks, n_rows, stats);
-  row_stats_finish_kernel<<<(unsigned)((n_cols + 127) / 128), 128, 0, st>>>(spart_c, p.stat_chunks, n_cols, stats_c);
+  if (!sym) row_stats_finish_kernel<<<(unsigned)((n_cols + 127) / 128), 128, 0, st>>>(spart_c, p.stat_chunks, n_cols, stats_c);
   DS_CUDA_TRY(cudaGetLastError());
 
   // GEMM: fp32 partials part[split][row][col]
   GemmParams gp = {};
   gp.splits = p.splits;
+  gp.sym = sym ? 1 : 0;
   gp.part = part;
   gp.part_split_stride = (int64_t)n_rows * n_cols;
   rc = launch_gemm_tn<GEMM_EPI_F32>(rows, n_rows, ld_rows, cols, n_cols, ld_cols, L, dtype, gp, st);
@@ -253,7 +274,7 @@ int ds_simmat(const void* rows, int64_t n_rows, int64_t ld_rows, const void* col
   const int64_t fblocks = ((n_cols + 255) / 256) * n_rows;
   if (fblocks > 0x7fffffffLL) return fail(DS_ERR_INVALID, "ds_simmat: matrix too large");
   simmat_finish_kernel<<<(unsigned)fblocks, 256, 0, st>>>(part, p.splits, (int64_t)n_rows * n_cols, n_rows, n_cols, stats, stats_c,
-                                            (double)L, mode, C, ldc);
+                                            (double)L, mode, C, ldc, sym ? 1 : 0);
   DS_CUDA_TRY(cudaGetLastError());
   return DS_OK;
 }

@@ -343,3 +343,23 @@ def test_simmat_self_is_symmetric_with_unit_diagonal():
     C = ops.simmat(f)
     assert (C.diagonal() - 1).abs().max().item() < 1e-5
     assert (C - C.t()).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize("n,L", [(300, 4096), (1000, 2048), (130, 200), (2032, 1024)])
+def test_simmat_symmetric_schedule_equals_the_full_one(n, L):
+    """rows == cols takes the upper-triangle tile schedule (about half the MMAs) and one statistics pass; the result must
+    agree with the general schedule and be exactly symmetric."""
+    dev = _cuda()
+    from diffsim_b200 import ops
+
+    g = torch.Generator().manual_seed(n + L)
+    f = (torch.randn(n, L, generator=g) * 0.8 + 0.1).half().to(dev)
+    for mode in ("cosine", "minmax_cosine"):
+        sym = ops.simmat(f, None, mode)
+        full = ops.simmat(f, f.clone(), mode)       # a different buffer: the general schedule
+        # the two schedules may cut L into different numbers of fp32 partials: equal up to that regrouping
+        assert (sym - full).abs().max().item() < 2e-5
+        assert torch.equal(sym, sym.t())            # mirrored, not recomputed
+    ref = O.simmat(f[:64].cpu(), f.cpu(), "cosine")
+    got = ops.simmat(f, None, "cosine")[:64].double().cpu()
+    assert (got - ref).abs().max().item() < 2e-4

@@ -93,3 +93,12 @@ def test_triplet_generator_has_near_ties_and_margins():
     assert len(images) == 18 and trips[2] == (6, 7, 8)
     images2, _ = synth.make_triplets(m, 6, torch.float16, seed=1)
     assert all(torch.equal(a[0], b[0]) for a, b in zip(images, images2))
+
+
+def test_hostbind_parses_sysfs_lists_and_never_raises():
+    from diffsim_b200 import hostbind
+
+    assert hostbind._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert hostbind._parse_cpulist("") == []
+    r = hostbind.bind_to_gpu_node(0)          # no GPU here: the affinity is left alone, with the reason stated
+    assert r["bound"] is False and isinstance(r["why"], str)
