@@ -89,6 +89,10 @@ int ds_profile_collect(float* total_ms, int* launches);
  * clocks CTA 0 spent in the last attention launch in word [8 x cap].  Returns 1 if tracing is compiled in, else 0.
  */
 int ds_debug_set_trace(void* dev_buf, int cap);
+/* Debug / A-B only: longest k range (in 64-element blocks, >= 8) one fp32 partial of ds_simmat may cover (default 256).
+ * Shorter ranges mean more partials (HBM traffic) but a smaller L2 working set and a shorter truncating accumulation
+ * chain.  Returns the value in force. */
+int ds_debug_set_simmat_max_kb(int kb);
 
 /* ---- K1: attention ------------------------------------------------------ */
 
