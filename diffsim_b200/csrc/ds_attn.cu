@@ -70,14 +70,18 @@ constexpr int kTmemOs = 416;     // O_self, packed 16-bit: [416, 416 + D_PAD/2)
 #define DS_MMA_WAIT 0        // waits of the MMA-issuing thread: 0 suspend hint, 1 try_wait without hint, 2 test_wait spin
 #endif
 #ifndef DS_POLY_STRIDE
-#define DS_POLY_STRIDE 0
+#define DS_POLY_STRIDE -1    // -1: per head dim (AttnCfg::POLY_STRIDE); >= 0 forces one value for every head dim (A/B builds)
 #endif
-constexpr int kPolyStride = DS_POLY_STRIDE;   // every n-th pair of exponentials on the FMA pipe (0: none)
 constexpr int kTmemL = 496;      // softmax denominators l = P . 1 (a 16-column MMA against a constant ones tile): [496,512)
 
 template <int D>
 struct AttnCfg {
   static constexpr int D_PAD = (D + 15) / 16 * 16;
+  // Every POLY_STRIDE-th pair of exponentials is evaluated with a degree-3 polynomial on the FMA pipe instead of MUFU
+  // (0: none).  With head dims <= 80 an item carries at most half the tensor work of D = 160 but the same 32 768
+  // exponentials, and long-kv streams of such items are MUFU-bound: measured +13% on SDXL (2,20,1024,64) / (2,10,4096,64),
+  // +6% on SD-1.5 up1 / up2, neutral on DiT-XL/2, and -4% at D = 160 (profiles/r1z_poly_shapes.txt).
+  static constexpr int POLY_STRIDE = DS_POLY_STRIDE >= 0 ? DS_POLY_STRIDE : (D <= 80 ? 3 : 0);
   static constexpr int SUBW = (D % 64 == 0) ? 64 : 32;           // elements per swizzle row
   static constexpr int SUB_BYTES = SUBW * 2;                      // 128 or 64: TMA box row == swizzle span
   static constexpr int NSUB = (D_PAD + SUBW - 1) / SUBW;
@@ -521,6 +525,7 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             f2_unpack(f2_fma(f2_pack_u(v[j], v[j + 1]), sl2_2, nm_2), x0, x1);
             // the MUFU pipe (16 ex2 / clk / SM) is what bounds this phase: every kPolyStride-th pair is evaluated on the
             // FMA pipe instead
+            constexpr int kPolyStride = C::POLY_STRIDE;
             if (kPolyStride > 0 && ((j >> 1) % (kPolyStride > 0 ? kPolyStride : 1)) == 0) {
               exp2_poly_f2(x0, x1, e0, e1);
             } else {
