@@ -244,7 +244,7 @@ int ds_profile_collect(float* total_ms, int* launches) {
 
 int ds_twoafc(const float* ab, const float* ac, int64_t n, int mode, int32_t* counts, uint8_t* flags,
               void* stream) {
-  if (!ab || !ac || !counts || n < 0) return ds::fail(DS_ERR_INVALID, "ds_twoafc: null pointer or negative n");
+  if (!counts || n < 0 || (n > 0 && (!ab || !ac))) return ds::fail(DS_ERR_INVALID, "ds_twoafc: null pointer or negative n");
   if (mode != DS_SIM_COSINE && mode != DS_SIM_MSE) return ds::fail(DS_ERR_INVALID, "ds_twoafc: bad mode %d", mode);
   int rc = ds_device_ok();
   if (rc != DS_OK) return rc;

@@ -216,6 +216,8 @@ def pair_reduce(x: torch.Tensor, y: torch.Tensor, similarity="cosine") -> torch.
     if x.shape != y.shape or x.dtype != y.dtype:
         raise RuntimeError("x and y must have the same shape and dtype")
     P = x.shape[0]
+    if P == 0:
+        return torch.empty(0, dtype=torch.float32, device=dev)
     x2, y2 = x.reshape(P, -1), y.reshape(P, -1)
     if x2.stride(1) != 1:
         x2 = x2.contiguous()
