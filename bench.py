@@ -373,7 +373,7 @@ def main():
         torch.cuda.synchronize(dev)
         k4_ms = e0.elapsed_time(e1) / 10
         k4_fl = 2.0 * hid_dev.shape[0] * B * S * (H * D) * (3 * H * D)
-        extra["roofline_k4"] = {"kernel": "gemm_tn_kernel<EPI_16> (QKV projection, tcgen05 128x256 tiles)", "bound": "tensor",
+        extra["roofline_k4"] = {"kernel": "gemm2_tn_kernel<EPI_16> (QKV projection, tcgen05 cta_group::2 256x256 tiles)", "bound": "tensor",
                                 "achieved": k4_fl / (k4_ms * 1e-3) / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                                 "frac": k4_fl / (k4_ms * 1e-3) / 1e12 / peaks["bf16_tflops"], "traffic": None,
                                 "flops_per_launch": k4_fl, "ms_per_launch": k4_ms, "images_per_launch": hid_dev.shape[0]}
@@ -438,15 +438,15 @@ def main():
         tm_n, tn_n = (Nf + 127) // 128, (Nf + 255) // 256
         tiles_exec = sum(max(0, tn_n - (tm * 128) // 256) for tm in range(tm_n))
         fl3 = 2.0 * tiles_exec * 128 * 256 * Lf
-        extra["roofline_k3"] = {"kernel": "simmat: row statistics + gemm_tn_kernel<EPI_F32> (upper-triangle tiles, split-K) + "
-                                          "normalise/mirror (N x N cosine)",
+        extra["roofline_k3"] = {"kernel": "simmat: row statistics + gemm2_tn_kernel<EPI_F32> (CTA pairs, 256x256 upper-triangle tiles, "
+                                          "split-K) + normalise/mirror (N x N cosine)",
                                 "bound": "tensor", "achieved": fl3 / (ms3 * 1e-3) / 1e12, "peak": peaks["bf16_tflops"],
                                 "unit": "TFLOP/s", "frac": fl3 / (ms3 * 1e-3) / 1e12 / peaks["bf16_tflops"], "traffic": None,
                                 "flops_per_launch": fl3, "flops_full_matrix": 2.0 * Nf * Nf * Lf, "ms_per_call": ms3,
                                 "images": Nf, "feature_len": Lf,
                                 "full_matrix_equivalent_tflops": 2.0 * Nf * Nf * Lf / (ms3 * 1e-3) / 1e12,
                                 "note": "whole ds_simmat call (one statistics pass + GEMM + finish); achieved counts the flops "
-                                        "EXECUTED (72 of 128 tiles), full_matrix_equivalent the 2*N*N*L of the result",
+                                        "EXECUTED (36 of 64 256x256 tiles), full_matrix_equivalent the 2*N*N*L of the result",
                                 "diag_minus_one_max": float((outm.diagonal() - 1).abs().max())}
         del feats, outm
 

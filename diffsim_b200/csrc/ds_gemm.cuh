@@ -39,6 +39,8 @@ struct GemmParams {
   int sym;                  // 1: C is symmetric (B == A): only tiles holding an element with row <= col are computed
   int tiles_used;           // tiles per split (tiles_m * tiles_n, or the upper-triangle count when sym)
   uint32_t idesc;
+  uint32_t idesc2;          // CTA-pair kernel: M = 256
+  int use_pair;             // -1 automatic (set by launch_gemm_tn's callers that leave it 0-initialised: see below), 0, 1
   // GEMM_EPI_F32: part[split][M][N] fp32
   float* part;
   int64_t part_split_stride;
@@ -52,9 +54,9 @@ struct GemmParams {
 
 // tiles of one split, n fastest.  Symmetric mode enumerates, row of tiles by row of tiles, only the tiles that hold an
 // element on or above the diagonal: tile (tm, tn) is needed iff tm * kGBM <= tn * kGBN + kGBN - 1, i.e. tn >= tm*kGBM / kGBN.
-__host__ __device__ __forceinline__ int gemm_sym_first_tn(int tm) { return (tm * kGBM) / kGBN; }
+__host__ __device__ __forceinline__ int gemm_sym_first_tn(int tm, int bm = kGBM) { return (tm * bm) / kGBN; }
 
-__device__ __forceinline__ void gemm_decode_tile(const GemmParams& p, int tile, int& tm, int& tn) {
+__device__ __forceinline__ void gemm_decode_tile(const GemmParams& p, int tile, int& tm, int& tn, int bm = kGBM) {
   if (!p.sym) {
     tm = tile / p.tiles_n;
     tn = tile - tm * p.tiles_n;
@@ -62,7 +64,7 @@ __device__ __forceinline__ void gemm_decode_tile(const GemmParams& p, int tile, 
   }
   tm = 0;
   for (;;) {
-    const int first = gemm_sym_first_tn(tm);
+    const int first = gemm_sym_first_tn(tm, bm);
     const int cnt = p.tiles_n - first;
     if (tile < cnt) {
       tn = first + tile;
@@ -73,13 +75,65 @@ __device__ __forceinline__ void gemm_decode_tile(const GemmParams& p, int tile, 
   }
 }
 
-static int gemm_sym_tile_count(int tiles_m, int tiles_n) {
+static int gemm_sym_tile_count(int tiles_m, int tiles_n, int bm = kGBM) {
   int n = 0;
   for (int tm = 0; tm < tiles_m; ++tm) {
-    const int cnt = tiles_n - gemm_sym_first_tn(tm);
+    const int cnt = tiles_n - gemm_sym_first_tn(tm, bm);
     if (cnt > 0) n += cnt;
   }
   return n;
+}
+
+// One thread's share of the epilogue: its accumulator row (TMEM lane) across the kGBN columns of the tile.
+template <int EPI, bool kBf16>
+__device__ __forceinline__ void gemm_epilogue_row(const GemmParams& p, uint32_t t_addr, int row, int n0, int split) {
+#pragma unroll 1
+  for (int c = 0; c < kGBN / 32; ++c) {
+    uint32_t v[32];
+    tmem_ld_x32(t_addr + c * 32, v);
+    tmem_wait_ld();
+    const int col0 = n0 + c * 32;
+    if (row < p.M && col0 < p.N) {
+      if constexpr (EPI == GEMM_EPI_F32) {
+        float* dst = p.part + (size_t)split * p.part_split_stride + (size_t)row * p.N + col0;
+        if (col0 + 32 <= p.N && (p.N & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                              __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) dst[j] = __uint_as_float(v[j]);
+        }
+      } else {
+        // 8-column groups: 16-byte stores; N, cols_per_out are multiples of 8 (checked by the host)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int col = col0 + g * 8;
+          if (col < p.N) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+            if (p.bias) {
+              const uint4 b4 = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.bias) + col));
+              const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 bf = unpack2<kBf16>(bw[j]);
+                f[2 * j] += bf.x;
+                f[2 * j + 1] += bf.y;
+              }
+            }
+            const int t = col / p.cols_per_out, cc = col - t * p.cols_per_out;
+            uint16_t* dst = static_cast<uint16_t*>(p.out[t]) + (size_t)row * p.ld_out[t] + cc;
+            *reinterpret_cast<uint4*>(dst) = make_uint4(pack2<kBf16>(f[0], f[1]), pack2<kBf16>(f[2], f[3]),
+                                                        pack2<kBf16>(f[4], f[5]), pack2<kBf16>(f[6], f[7]));
+          }
+        }
+      }
+    }
+}
 }
 
 template <int EPI, bool kBf16>
@@ -189,53 +243,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int row = tm * kGBM + quad * 32 + lane;
       const int n0 = tn * kGBN;
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kGBN;
-#pragma unroll 1
-      for (int c = 0; c < kGBN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_x32(t_addr + c * 32, v);
-        tmem_wait_ld();
-        const int col0 = n0 + c * 32;
-        if (row < p.M && col0 < p.N) {
-          if constexpr (EPI == GEMM_EPI_F32) {
-            float* dst = p.part + (size_t)split * p.part_split_stride + (size_t)row * p.N + col0;
-            if (col0 + 32 <= p.N && (p.N & 3) == 0) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                                  __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) dst[j] = __uint_as_float(v[j]);
-            }
-          } else {
-            // 8-column groups: 16-byte stores; N, cols_per_out are multiples of 8 (checked by the host)
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int col = col0 + g * 8;
-              if (col < p.N) {
-                float f[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-                if (p.bias) {
-                  const uint4 b4 = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.bias) + col));
-                  const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float2 bf = unpack2<kBf16>(bw[j]);
-                    f[2 * j] += bf.x;
-                    f[2 * j + 1] += bf.y;
-                  }
-                }
-                const int t = col / p.cols_per_out, cc = col - t * p.cols_per_out;
-                uint16_t* dst = static_cast<uint16_t*>(p.out[t]) + (size_t)row * p.ld_out[t] + cc;
-                *reinterpret_cast<uint4*>(dst) = make_uint4(pack2<kBf16>(f[0], f[1]), pack2<kBf16>(f[2], f[3]),
-                                                            pack2<kBf16>(f[4], f[5]), pack2<kBf16>(f[6], f[7]));
-              }
-            }
-          }
-        }
-      }
+      gemm_epilogue_row<EPI, kBf16>(p, t_addr, row, n0, split);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -244,6 +252,146 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant: one cluster of two CTAs per 256 x 256 output tile (tcgen05.mma.cta_group::2, M = 256).
+// Each CTA streams its own 128 rows of A and HALF of the B tile (128 of the 256 rows): per 64-wide k block it writes
+// 32 KB and its tensor core reads 32 KB of its own shared memory -- 125 B/clk against the 128 B/clk port, where the
+// 1-CTA shape needs 188 -- and the ring holds 6 stages instead of 4.  The leader (cluster rank 0) issues the MMAs for
+// both; completion is multicast to the barriers of both CTAs; each CTA's epilogue drains its own 128 accumulator rows.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kG2BM = 256;                          // rows per cluster tile (128 per CTA)
+constexpr int kG2Stages = 6;
+constexpr int kG2BHalfBytes = (kGBN / 2) * kGBK * 2;   // 16 KB: this CTA's half of the B tile
+constexpr int kG2StageBytes = kGABytes + kG2BHalfBytes;
+constexpr size_t kG2SmemBytes = 1024 + (size_t)kG2Stages * kG2StageBytes + 256;
+
+template <int EPI, bool kBf16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGThreads, 1)
+gemm2_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kG2Stages * kG2StageBytes);
+  uint64_t* full = bars;                              // leader's copy counts the bytes of both CTAs
+  uint64_t* empty = bars + kG2Stages;                 // each CTA's copy is signalled by the multicast commit
+  uint64_t* acc_full = bars + 2 * kG2Stages;          // [2] multicast commit
+  uint64_t* acc_empty = bars + 2 * kG2Stages + 2;     // [2] leader's copy: 8 arrivals (4 epilogue warps x 2 CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kG2Stages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kG2Stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(tmem_slot, 512);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before_sync();
+  cluster_sync_all();            // barriers of BOTH CTAs are initialised before anyone signals across the pair
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles = p.tiles_used;
+  const int n_units = tiles * p.splits;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = cluster_id; u < n_units; u += n_clusters) {
+        const int split = u / tiles, tile = u - split * tiles;
+        int tm, tn;
+        gemm_decode_tile(p, tile, tm, tn, kG2BM);
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* a = smem + (size_t)stage * kG2StageBytes;
+          if (leader) mbar_arrive_expect_tx(&full[stage], 2 * kG2StageBytes);
+          tma_load_2d_2cta(a, &map_a, &full[stage], kb * kGBK, tm * kG2BM + (int)rank * kGBM);
+          tma_load_2d_2cta(a + kGABytes, &map_b, &full[stage], kb * kGBK, tn * kGBN + (int)rank * (kGBN / 2));
+          if (++stage == kG2Stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0, n_local = 0;
+      for (int u = cluster_id; u < n_units; u += n_clusters, ++n_local) {
+        const int split = u / tiles;
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const uint32_t buf = n_local & 1u;
+        mbar_wait(&acc_empty[buf], ((n_local >> 1) & 1u) ^ 1u);   // both epilogues have drained this accumulator
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + buf * kGBN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * kG2StageBytes);
+          const uint64_t a_desc = umma_smem_desc(a_addr, 16, 1024, UMMA_SW128);
+          const uint64_t b_desc = umma_smem_desc(a_addr + kGABytes, 16, 1024, UMMA_SW128);
+#pragma unroll
+          for (int k = 0; k < kGBK / 16; ++k)
+            umma_f16_ss_2cta(d_tmem, a_desc + 2 * k, b_desc + 2 * k, p.idesc2, (kb > kb0 || k > 0) ? 1u : 0u);
+          umma_commit_2cta(&empty[stage]);
+          if (++stage == kG2Stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2cta(&acc_full[buf]);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    uint32_t n_local = 0;
+    for (int u = cluster_id; u < n_units; u += n_clusters, ++n_local) {
+      const int split = u / tiles, tile = u - split * tiles;
+      int tm, tn;
+      gemm_decode_tile(p, tile, tm, tn, kG2BM);
+      const uint32_t buf = n_local & 1u;
+      mbar_wait(&acc_full[buf], (n_local >> 1) & 1u);
+      tc_fence_after_sync();
+      const int row = tm * kG2BM + (int)rank * kGBM + quad * 32 + lane;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kGBN;
+      gemm_epilogue_row<EPI, kBf16>(p, t_addr, row, tn * kGBN, split);
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&acc_empty[buf]);
+    }
+  }
+  tc_fence_before_sync();
+  cluster_sync_all();            // the peer may still be reading this CTA's B half / signalling its barriers
+  if (warp == 1) tmem_dealloc_2cta(tmem_base, 512);
+}
+
+// Which kernel serves a problem: the debug override (ds_debug_set_gemm_variant: -1 automatic, 0 1-CTA only, 2 pairs always),
+// else the caller's choice (GemmParams::use_pair: 0 / 1), else pairs when the 256 x 256 tiles fill the clusters twice over.
+static bool gemm_use_pair(int64_t M, int64_t N, int splits, int use_pair) {
+  if (g_gemm_variant == 0) return false;
+  if (g_gemm_variant == 2) return true;
+  if (use_pair >= 0) return use_pair != 0;
+  const int64_t tiles2 = ((M + kG2BM - 1) / kG2BM) * ((N + kGBN - 1) / kGBN);
+  return tiles2 * (splits < 1 ? 1 : splits) >= 2 * (sm_count() / 2);
 }
 
 // Host side: tensor maps + launch.  a: [M, K] with leading dimension lda (elements), b: [N, K] with ldb.
@@ -264,6 +412,37 @@ static int launch_gemm_tn(const void* a, int64_t M, int64_t lda, const void* b, 
   }
   p.M = (int)M;
   p.N = (int)N;
+  // CTA pairs (256 x 256 tiles) when there are enough of them to fill the 74 clusters; small problems keep the 1-CTA shape
+  const bool pair = gemm_use_pair(M, N, p.splits, p.use_pair);
+  if (pair) {
+    uint64_t dimsb2[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t strb2[1] = {(uint64_t)ldb * 2};
+    uint32_t boxb2[2] = {(uint32_t)kGBK, (uint32_t)(kGBN / 2)};
+    if ((rc = encode_tensor_map(&map_b, dtype, 2, b, dimsb2, strb2, boxb2, 128)) != DS_OK) return rc;
+    p.tiles_m = (int)((M + kG2BM - 1) / kG2BM);
+    p.tiles_n = (int)((N + kGBN - 1) / kGBN);
+    p.kb_total = (int)((K + kGBK - 1) / kGBK);
+    if (p.splits < 1) p.splits = 1;
+    p.kb_per_split = (p.kb_total + p.splits - 1) / p.splits;
+    p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+    p.idesc2 = umma_idesc_f16(dtype == DS_BF16 ? 1u : 0u, kG2BM, kGBN, 0, 0);
+    if (p.sym && (M != N || a != b || lda != ldb)) return fail(DS_ERR_INVALID, "gemm: symmetric mode needs B == A");
+    p.tiles_used = p.sym ? gemm_sym_tile_count(p.tiles_m, p.tiles_n, kG2BM) : p.tiles_m * p.tiles_n;
+    const int64_t units2 = (int64_t)p.tiles_used * p.splits;
+    if (units2 <= 0) return DS_OK;
+    if (units2 > INT32_MAX) return fail(DS_ERR_INVALID, "gemm: too many work units");
+    int clusters = sm_count() / 2;
+    if (units2 < clusters) clusters = (int)units2;
+    if (dtype == DS_BF16) {
+      DS_CUDA_TRY(cudaFuncSetAttribute(gemm2_tn_kernel<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG2SmemBytes));
+      gemm2_tn_kernel<EPI, true><<<2 * clusters, kGThreads, kG2SmemBytes, st>>>(map_a, map_b, p);
+    } else {
+      DS_CUDA_TRY(cudaFuncSetAttribute(gemm2_tn_kernel<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG2SmemBytes));
+      gemm2_tn_kernel<EPI, false><<<2 * clusters, kGThreads, kG2SmemBytes, st>>>(map_a, map_b, p);
+    }
+    DS_CUDA_TRY(cudaGetLastError());
+    return DS_OK;
+  }
   p.tiles_m = (int)((M + kGBM - 1) / kGBM);
   p.tiles_n = (int)((N + kGBN - 1) / kGBN);
   p.kb_total = (int)((K + kGBK - 1) / kGBK);

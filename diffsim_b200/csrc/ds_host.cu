@@ -9,6 +9,9 @@
 
 namespace ds {
 
+int g_gemm_variant = -1;
+
+
 static thread_local char g_err[512] = "";
 
 void set_error(const char* fmt, ...) {
@@ -240,6 +243,11 @@ int ds_profile_collect(float* total_ms, int* launches) {
   *launches = ds::g_prof.n;
   ds::g_prof.n = 0;
   return DS_OK;
+}
+
+int ds_debug_set_gemm_variant(int variant) {
+  ds::g_gemm_variant = variant;
+  return 0;
 }
 
 int ds_twoafc(const float* ab, const float* ac, int64_t n, int mode, int32_t* counts, uint8_t* flags,

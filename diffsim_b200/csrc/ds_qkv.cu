@@ -39,6 +39,7 @@ int ds_qkv_project(const void* hidden, int64_t n_rows, int64_t ld_hidden, int64_
   int rc = ds_device_ok();
   if (rc != DS_OK) return rc;
   gp.splits = 1;
+  gp.use_pair = -1;
   gp.cols_per_out = (int)cols_per_out;
   gp.bias = bias;
   return launch_gemm_tn<GEMM_EPI_16>(hidden, n_rows, ld_hidden, weight, n_out, ld_weight, c_in, dtype, gp,

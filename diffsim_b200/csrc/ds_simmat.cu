@@ -145,20 +145,25 @@ static int g_simmat_max_kb = 256;   // ds_debug_set_simmat_max_kb (A/B)
 
 struct SimmatPlan {
   int tiles_m, tiles_n, kb_total, splits, kb_per_split;
+  int pair;   // 1: CTA-pair kernel (256 x 256 tiles, 74 clusters)
   int stat_chunks;
   int64_t stat_chunk_elems;
 };
 
 static SimmatPlan simmat_plan(int64_t n_rows, int64_t n_cols, int64_t L, bool sym = false) {
   SimmatPlan p;
-  p.tiles_m = (int)((n_rows + kGBM - 1) / kGBM);
+  // CTA pairs when both extents are at least two 256-wide tiles (else the 128-row tiles waste less)
+  p.pair = (g_gemm_variant == 2 || (g_gemm_variant != 0 && n_rows >= 2 * kG2BM && n_cols >= 2 * kGBN)) ? 1 : 0;
+  const int bm = p.pair ? kG2BM : kGBM;
+  p.tiles_m = (int)((n_rows + bm - 1) / bm);
   p.tiles_n = (int)((n_cols + kGBN - 1) / kGBN);
   p.kb_total = (int)((L + kGBK - 1) / kGBK);
   // split along L: the smallest split count whose work units (tiles x splits) fill whole waves of the persistent grid
   // to >= 95% (at least 8 k blocks per unit, at most 64 splits: the fp32 partials cost HBM traffic)
-  const int64_t tiles = sym ? gemm_sym_tile_count(p.tiles_m, p.tiles_n) : (int64_t)p.tiles_m * p.tiles_n;
+  const int64_t tiles = sym ? gemm_sym_tile_count(p.tiles_m, p.tiles_n, bm) : (int64_t)p.tiles_m * p.tiles_n;
   int sms = sm_count();
   if (sms <= 0) sms = 148;
+  if (p.pair) sms /= 2;   // work units are dealt to clusters
   // accuracy: the tensor core adds each K = 16 MMA into the fp32 accumulator with truncation, a bias that grows with the
   // length of the chain (measured on 655 360-long unit-cosine rows: 2.1e-3 at 20 480 MMAs per partial, 5e-4 at 1 100);
   // a partial therefore never covers more than kMaxKbPerSplit k blocks (1024 MMAs); the partials are added in double
@@ -273,6 +278,7 @@ int ds_simmat(const void* rows, int64_t n_rows, int64_t ld_rows, const void* col
   GemmParams gp = {};
   gp.splits = p.splits;
   gp.sym = sym ? 1 : 0;
+  gp.use_pair = p.pair;
   gp.part = part;
   gp.part_split_stride = (int64_t)n_rows * n_cols;
   rc = launch_gemm_tn<GEMM_EPI_F32>(rows, n_rows, ld_rows, cols, n_cols, ld_cols, L, dtype, gp, st);

@@ -89,6 +89,9 @@ int ds_profile_collect(float* total_ms, int* launches);
  * clocks CTA 0 spent in the last attention launch in word [8 x cap].  Returns 1 if tracing is compiled in, else 0.
  */
 int ds_debug_set_trace(void* dev_buf, int cap);
+/* Debug / A-B only: GEMM kernel behind ds_qkv_project and ds_simmat: -1 automatic (default), 0 the 1-CTA 128x256 kernel
+ * only, 2 the CTA-pair (cta_group::2, 256x256) kernel always. */
+int ds_debug_set_gemm_variant(int variant);
 /* Debug / A-B only: longest k range (in 64-element blocks, >= 8) one fp32 partial of ds_simmat may cover (default 256).
  * Shorter ranges mean more partials (HBM traffic) but a smaller L2 working set and a shorter truncating accumulation
  * chain.  Returns the value in force. */
