@@ -120,3 +120,74 @@ class B200AttnProcessor:
             hidden_states = hidden_states + residual
         hidden_states = hidden_states / getattr(attn, "rescale_output_factor", 1.0)
         return hidden_states, query, key, value, residual
+
+
+class B200IPAdapterAttnProcessor(torch.nn.Module):
+    """hacked_IPAdapterAttnProcessor2_0 (diffsim/hacked_attn.py:104-335) with its attentions on the sm_100a kernel.
+
+    Same constructor (`hidden_size, cross_attention_dim, dtype, num_tokens, scale`), the same `to_k_ip` / `to_v_ip`
+    ModuleLists (so IP-Adapter state dicts load unchanged) and the hacked 5-tuple return
+    `(hidden_states, query, ip_keys, ip_values, residual)` (:335).  `encoder_hidden_states` is the tuple
+    `(text_states, [ip_states_i])` (:161-162) or, deprecated, one tensor whose last `num_tokens[0]` rows are the image
+    tokens (:163-173).  The text cross-attention and one attention per adapter against its image-prompt tokens
+    (kv length 4 / 16: a ragged tail for the kernel) are added with the adapter scales (:311-320).  IP-adapter masks
+    (:225-280) are a generation feature the scorer never passes: NotImplementedError, not a silent skip."""
+
+    def __init__(self, hidden_size, cross_attention_dim=None, dtype=torch.float16, num_tokens=(4,), scale=1.0):
+        super().__init__()
+        self.hidden_size, self.cross_attention_dim = hidden_size, cross_attention_dim
+        if not isinstance(num_tokens, (tuple, list)):
+            num_tokens = [num_tokens]
+        self.num_tokens = num_tokens
+        if not isinstance(scale, list):
+            scale = [scale] * len(num_tokens)
+        if len(scale) != len(num_tokens):
+            raise ValueError("`scale` should be a list of integers with the same length as `num_tokens`.")
+        self.scale = scale
+        mk = lambda: torch.nn.ModuleList([torch.nn.Linear(cross_attention_dim, hidden_size, bias=False, dtype=dtype)  # noqa: E731
+                                          for _ in range(len(num_tokens))])
+        self.to_k_ip, self.to_v_ip = mk(), mk()
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0,
+                 ip_adapter_masks=None):
+        if attention_mask is not None or ip_adapter_masks is not None:
+            raise NotImplementedError("attention / ip-adapter masks are not used on the DiffSim path")
+        residual = hidden_states
+        ip_hidden_states = None
+        if encoder_hidden_states is not None:
+            if isinstance(encoder_hidden_states, tuple):
+                encoder_hidden_states, ip_hidden_states = encoder_hidden_states
+            else:
+                end_pos = encoder_hidden_states.shape[1] - self.num_tokens[0]
+                encoder_hidden_states, ip_hidden_states = (encoder_hidden_states[:, :end_pos, :],
+                                                           [encoder_hidden_states[:, end_pos:, :]])
+        if ip_hidden_states is None:
+            raise ValueError("the IP-Adapter processor needs image-prompt states in encoder_hidden_states")
+        if getattr(attn, "spatial_norm", None) is not None:
+            hidden_states = attn.spatial_norm(hidden_states, temb)
+        input_ndim = hidden_states.ndim
+        if input_ndim == 4:
+            batch_size, channel, height, width = hidden_states.shape
+            hidden_states = hidden_states.view(batch_size, channel, height * width).transpose(1, 2)
+        batch_size = hidden_states.shape[0]
+        query, key, value = project_qkv(attn, hidden_states, encoder_hidden_states)
+        head_dim = query.shape[-1]
+        merge = lambda o: o.transpose(1, 2).reshape(batch_size, -1, attn.heads * head_dim).to(query.dtype)  # noqa: E731
+        hidden_states = merge(ops.attn_fwd(query, key, value))
+        ip_keys, ip_values = [], []
+        for ip_states, s, to_k_ip, to_v_ip in zip(ip_hidden_states, self.scale, self.to_k_ip, self.to_v_ip):
+            if (isinstance(s, list) and all(x == 0 for x in s)) or (not isinstance(s, list) and s == 0):
+                continue
+            ip_key = split_heads(to_k_ip(ip_states), attn.heads)
+            ip_value = split_heads(to_v_ip(ip_states), attn.heads)
+            ip_keys.append(ip_key)
+            ip_values.append(ip_value)
+            hidden_states = hidden_states + s * merge(ops.attn_fwd(query, ip_key, ip_value))
+        hidden_states = attn.to_out[0](hidden_states)
+        hidden_states = attn.to_out[1](hidden_states)
+        if input_ndim == 4:
+            hidden_states = hidden_states.transpose(-1, -2).reshape(batch_size, channel, height, width)
+        if getattr(attn, "residual_connection", False):
+            hidden_states = hidden_states + residual
+        hidden_states = hidden_states / getattr(attn, "rescale_output_factor", 1.0)
+        return hidden_states, query, ip_keys, ip_values, residual

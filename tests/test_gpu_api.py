@@ -132,3 +132,52 @@ def test_host_scorer_equals_device_scorer():
     got = scorer.score(host, T)
     assert got == (int(counts[0]), int(counts[1]))
     assert scorer.h2d_bytes == 3 * T * cache.bytes_per_image and scorer.d2h_bytes == 8
+
+
+def test_ip_adapter_processor_follows_the_reference_contract():
+    """B200IPAdapterAttnProcessor vs a torch restatement of hacked_IPAdapterAttnProcessor2_0.__call__ (diffsim/hacked_attn.py:
+    146-335, unmasked path): same 5-tuple, ip keys / values as head-split views, hidden states within fp16 tolerance; the
+    returned (query, ip_keys, ip_values) then score through aas_score_ip_adapter."""
+    dev = _cuda()
+    import torch.nn.functional as F
+
+    from diffsim_b200 import hooks
+    from diffsim_b200.diffsim import aas_score_ip_adapter
+
+    torch.manual_seed(1)
+    C, heads, T_text, T_ip = 1280, 8, 77, 16
+    attn = _FakeAttention(C, heads, torch.float16, dev)
+    proc = hooks.B200IPAdapterAttnProcessor(C, C, torch.float16, num_tokens=(T_ip,), scale=0.7).to(dev)
+    assert [tuple(m.weight.shape) for m in proc.to_k_ip] == [(C, C)]
+
+    def ref_call(x, text, ip):
+        q = attn.to_q(x).view(2, -1, heads, C // heads).transpose(1, 2)
+        k = attn.to_k(text).view(2, -1, heads, C // heads).transpose(1, 2)
+        v = attn.to_v(text).view(2, -1, heads, C // heads).transpose(1, 2)
+        h = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(2, -1, C)
+        ik = proc.to_k_ip[0](ip).view(2, -1, heads, C // heads).transpose(1, 2)
+        iv = proc.to_v_ip[0](ip).view(2, -1, heads, C // heads).transpose(1, 2)
+        h = h + 0.7 * F.scaled_dot_product_attention(q, ik, iv).transpose(1, 2).reshape(2, -1, C)
+        return attn.to_out[0](h), q, ik, iv
+
+    outs = []
+    for seed in (0, 1):
+        g = torch.Generator(device=dev).manual_seed(seed)
+        x = torch.randn(2, 256, C, device=dev, dtype=torch.float16, generator=g)
+        text = torch.randn(2, T_text, C, device=dev, dtype=torch.float16, generator=g)
+        ip = torch.randn(2, T_ip, C, device=dev, dtype=torch.float16, generator=g)
+        hs, q, ipk, ipv, res = proc(attn, x, encoder_hidden_states=(text, [ip]))
+        ref_h, ref_q, ref_k, ref_v = ref_call(x, text, ip)
+        assert res is x and len(ipk) == len(ipv) == 1
+        assert ipk[0].shape == (2, heads, T_ip, C // heads) and ipk[0].stride(-1) == 1
+        assert torch.equal(q, ref_q) and torch.equal(ipk[0], ref_k) and torch.equal(ipv[0], ref_v)
+        assert (hs.float() - ref_h.float()).abs().max().item() < 3e-2
+        # deprecated single-tensor form: the last num_tokens rows are the image tokens (hacked_attn.py:163-173)
+        hs2, *_ = proc(attn, x, encoder_hidden_states=torch.cat([text, ip], dim=1))
+        assert torch.equal(hs2, hs)
+        outs.append((q, ipk, ipv))
+    s = aas_score_ip_adapter(outs[0], outs[1], "cosine", match_reference_dtype=False)
+    same = aas_score_ip_adapter(outs[0], outs[0], "cosine", match_reference_dtype=False)
+    assert float(same) == pytest.approx(1.0, abs=1e-5) and -1.0 <= float(s) < 1.0
+    with pytest.raises(NotImplementedError):
+        proc(attn, x, encoder_hidden_states=(text, [ip]), ip_adapter_masks=[torch.ones(1, 1, 16, 16, device=dev)])
