@@ -373,7 +373,7 @@ def main():
         torch.cuda.synchronize(dev)
         k4_ms = e0.elapsed_time(e1) / 10
         k4_fl = 2.0 * hid_dev.shape[0] * B * S * (H * D) * (3 * H * D)
-        extra["roofline_k4"] = {"kernel": "gemm2_tn_kernel<EPI_16> (QKV projection, tcgen05 cta_group::2 256x256 tiles)", "bound": "tensor",
+        extra["roofline_k4"] = {"kernel": "gemm2_tn_kernel<EPI_16> (QKV projection, tcgen05 cta_group::2 256x256 tiles, TMA-store epilogue)", "bound": "tensor",
                                 "achieved": k4_fl / (k4_ms * 1e-3) / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                                 "frac": k4_fl / (k4_ms * 1e-3) / 1e12 / peaks["bf16_tflops"], "traffic": None,
                                 "flops_per_launch": k4_fl, "ms_per_launch": k4_ms, "images_per_launch": hid_dev.shape[0]}

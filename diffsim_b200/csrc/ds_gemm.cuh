@@ -40,6 +40,7 @@ struct GemmParams {
   int tiles_used;           // tiles per split (tiles_m * tiles_n, or the upper-triangle count when sym)
   uint32_t idesc;
   uint32_t idesc2;          // CTA-pair kernel: M = 256
+  int tma_store;            // CTA-pair kernel, 16-bit outputs: epilogue through TMA stores (GemmOutMaps)
   int use_pair;             // -1 automatic (set by launch_gemm_tn's callers that leave it 0-initialised: see below), 0, 1
   // GEMM_EPI_F32: part[split][M][N] fp32
   float* part;
@@ -291,6 +292,70 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// Tensor maps of the (up to three) 16-bit output tensors, [M rows, cols_per_out] with their own row strides; box = 64
+// columns x 32 rows, 128-byte swizzle (the layout the epilogue's staging patch already has).
+struct GemmOutMaps {
+  CUtensorMap m[3];
+};
+
+// Epilogue of one warp through TMA stores: 32 rows x 64 columns per pass go registers -> swizzled 4 KB patch (two per
+// warp, alternating) -> one cp.async.bulk.tensor store issued by lane 0.  The copy engine reads the patch and writes
+// full lines; rows past M and columns past the tensor are clipped by the hardware.  `pass` counts this warp's passes.
+template <bool kBf16>
+__device__ __forceinline__ void gemm_epilogue_rows_tma(const GemmParams& p, const GemmOutMaps& om, uint32_t t_addr, int row0,
+                                                       int n0, uint8_t* patches, int lane, uint32_t& pass) {
+#pragma unroll 1
+  for (int ps = 0; ps < kGBN / 64; ++ps, ++pass) {
+    const int col0 = n0 + ps * 64;
+    if (col0 >= p.N) break;                               // warp-uniform
+    uint8_t* patch = patches + (pass & 1u) * kGEpiStageBytes;
+    const uint32_t st_base = smem_u32(patch);
+    // the store issued two passes ago has finished reading this patch
+    if (lane == 0) tma_store_wait_read<1>();
+    __syncwarp();
+    uint32_t w[32];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t v[32];
+      tmem_ld_x32(t_addr + ps * 64 + half * 32, v);
+      tmem_wait_ld();
+      const int cb = col0 + half * 32;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+        if (p.bias && cb + g * 8 < p.N) {
+          const uint4 b4 = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.bias) + cb + g * 8));
+          const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 bf = unpack2<kBf16>(bw[j]);
+            f[2 * j] += bf.x;
+            f[2 * j + 1] += bf.y;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[half * 16 + g * 4 + j] = pack2<kBf16>(f[2 * j], f[2 * j + 1]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const uint32_t a = st_base + (uint32_t)lane * 128u + (uint32_t)((u ^ (lane & 7)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w[4 * u]), "r"(w[4 * u + 1]), "r"(w[4 * u + 2]),
+                   "r"(w[4 * u + 3])
+                   : "memory");
+    }
+    fence_proxy_async_smem();      // generic-proxy writes -> visible to the copy engine
+    __syncwarp();
+    if (lane == 0) {
+      const int t = col0 / p.cols_per_out;                // cols_per_out % 64 == 0: one tensor per pass
+      tma_store_2d(&om.m[t], patch, col0 - t * p.cols_per_out, row0);
+      tma_store_commit();
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // CTA-pair variant: one cluster of two CTAs per 256 x 256 output tile (tcgen05.mma.cta_group::2, M = 256).
 // Each CTA streams its own 128 rows of A and HALF of the B tile (128 of the 256 rows): per 64-wide k block it writes
@@ -302,11 +367,12 @@ constexpr int kG2BM = 256;                          // rows per cluster tile (12
 constexpr int kG2Stages = 6;
 constexpr int kG2BHalfBytes = (kGBN / 2) * kGBK * 2;   // 16 KB: this CTA's half of the B tile
 constexpr int kG2StageBytes = kGABytes + kG2BHalfBytes;
-constexpr size_t kG2SmemBytes = 1024 + (size_t)kG2Stages * kG2StageBytes + 256 + 4 * 4096;
+constexpr size_t kG2SmemBytes = 1024 + (size_t)kG2Stages * kG2StageBytes + 1024 + 8 * 4096;   // ring | barriers | 2 patches per epilogue warp
 
 template <int EPI, bool kBf16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGThreads, 1)
-gemm2_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
+gemm2_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                const __grid_constant__ GemmOutMaps omaps, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kG2Stages * kG2StageBytes);
@@ -315,7 +381,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   uint64_t* acc_full = bars + 2 * kG2Stages;          // [2] multicast commit
   uint64_t* acc_empty = bars + 2 * kG2Stages + 2;     // [2] leader's copy: 8 arrivals (4 epilogue warps x 2 CTAs)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kG2Stages + 4);
-  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 256;   // 4 x 4 KB, 128-byte aligned
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 1024;  // 4 warps x 2 x 4 KB, 1024-byte aligned (swizzle atoms)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -401,7 +467,8 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
   } else {
     const int quad = warp & 3;
-    uint32_t n_local = 0;
+    uint32_t n_local = 0, pass = 0;
+    uint8_t* my_patches = epi_stage + (warp - 2) * 2 * kGEpiStageBytes;
     for (int u = cluster_id; u < n_units; u += n_clusters, ++n_local) {
       const int split = u / tiles, tile = u - split * tiles;
       int tm, tn;
@@ -410,12 +477,18 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       mbar_wait(&acc_full[buf], (n_local >> 1) & 1u);
       tc_fence_after_sync();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kGBN;
-      gemm_epilogue_rows<EPI, kBf16>(p, t_addr, tm * kG2BM + (int)rank * kGBM + quad * 32, tn * kGBN, split,
-                                     epi_stage + (warp - 2) * kGEpiStageBytes, lane);
+      const int row0 = tm * kG2BM + (int)rank * kGBM + quad * 32;
+      if constexpr (EPI == GEMM_EPI_16) {
+        if (p.tma_store) gemm_epilogue_rows_tma<kBf16>(p, omaps, t_addr, row0, tn * kGBN, my_patches, lane, pass);
+        else gemm_epilogue_rows<EPI, kBf16>(p, t_addr, row0, tn * kGBN, split, my_patches, lane);
+      } else {
+        gemm_epilogue_rows<EPI, kBf16>(p, t_addr, row0, tn * kGBN, split, my_patches, lane);
+      }
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&acc_empty[buf]);
     }
+    if (lane == 0) tma_store_wait_all();   // outstanding bulk stores complete before the CTA retires
   }
   tc_fence_before_sync();
   cluster_sync_all();            // the peer may still be reading this CTA's B half / signalling its barriers
@@ -471,12 +544,25 @@ static int launch_gemm_tn(const void* a, int64_t M, int64_t lda, const void* b, 
     if (units2 > INT32_MAX) return fail(DS_ERR_INVALID, "gemm: too many work units");
     int clusters = sm_count() / 2;
     if (units2 < clusters) clusters = (int)units2;
+    GemmOutMaps om;
+    memset(&om, 0, sizeof(om));
+    p.tma_store = 0;
+    if (EPI == GEMM_EPI_16 && g_gemm_tma_store && p.cols_per_out % 64 == 0) {
+      const int n_t = (int)(N / p.cols_per_out);
+      p.tma_store = 1;
+      for (int t = 0; t < n_t && t < 3; ++t) {
+        uint64_t od[2] = {(uint64_t)p.cols_per_out, (uint64_t)M};
+        uint64_t os[1] = {(uint64_t)p.ld_out[t] * 2};
+        uint32_t ob[2] = {64u, 32u};
+        if ((rc = encode_tensor_map(&om.m[t], dtype, 2, p.out[t], od, os, ob, 128)) != DS_OK) return rc;
+      }
+    }
     if (dtype == DS_BF16) {
       DS_CUDA_TRY(cudaFuncSetAttribute(gemm2_tn_kernel<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG2SmemBytes));
-      gemm2_tn_kernel<EPI, true><<<2 * clusters, kGThreads, kG2SmemBytes, st>>>(map_a, map_b, p);
+      gemm2_tn_kernel<EPI, true><<<2 * clusters, kGThreads, kG2SmemBytes, st>>>(map_a, map_b, om, p);
     } else {
       DS_CUDA_TRY(cudaFuncSetAttribute(gemm2_tn_kernel<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG2SmemBytes));
-      gemm2_tn_kernel<EPI, false><<<2 * clusters, kGThreads, kG2SmemBytes, st>>>(map_a, map_b, p);
+      gemm2_tn_kernel<EPI, false><<<2 * clusters, kGThreads, kG2SmemBytes, st>>>(map_a, map_b, om, p);
     }
     DS_CUDA_TRY(cudaGetLastError());
     return DS_OK;

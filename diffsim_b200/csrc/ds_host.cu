@@ -10,6 +10,7 @@
 namespace ds {
 
 int g_gemm_variant = -1;
+int g_gemm_tma_store = 1;
 
 
 static thread_local char g_err[512] = "";
@@ -246,7 +247,17 @@ int ds_profile_collect(float* total_ms, int* launches) {
 }
 
 int ds_debug_set_gemm_variant(int variant) {
-  ds::g_gemm_variant = variant;
+  // variants -1 / 0 / 2; adding 16 to 0 or 2 (or passing -17 for "automatic") turns the TMA-store epilogue off
+  if (variant == -17) {
+    ds::g_gemm_variant = -1;
+    ds::g_gemm_tma_store = 0;
+  } else if (variant >= 16) {
+    ds::g_gemm_variant = variant - 16;
+    ds::g_gemm_tma_store = 0;
+  } else {
+    ds::g_gemm_variant = variant;
+    ds::g_gemm_tma_store = 1;
+  }
   return 0;
 }
 

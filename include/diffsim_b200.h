@@ -90,7 +90,8 @@ int ds_profile_collect(float* total_ms, int* launches);
  */
 int ds_debug_set_trace(void* dev_buf, int cap);
 /* Debug / A-B only: GEMM kernel behind ds_qkv_project and ds_simmat: -1 automatic (default), 0 the 1-CTA 128x256 kernel
- * only, 2 the CTA-pair (cta_group::2, 256x256) kernel always. */
+ * only, 2 the CTA-pair (cta_group::2, 256x256) kernel always.  Adding 16 to 0 / 2 (or passing -17 for automatic) selects
+ * the epilogue without TMA stores. */
 int ds_debug_set_gemm_variant(int variant);
 /* Debug / A-B only: longest k range (in 64-element blocks, >= 8) one fp32 partial of ds_simmat may cover (default 256).
  * Shorter ranges mean more partials (HBM traffic) but a smaller L2 working set and a shorter truncating accumulation
