@@ -95,6 +95,10 @@ def load() -> C.CDLL:
             fn.argtypes = args
         if lib.ds_abi_version() != 1:
             raise RuntimeError(f"ABI mismatch: library reports version {lib.ds_abi_version()}, binding expects 1")
+        # A/B switches for whole-process runs (bench.py under tools/gpu_ab.sh): DIFFSIM_B200_DEBUG="gemm_variant=0,simmat_max_kb=128"
+        for item in filter(None, os.environ.get("DIFFSIM_B200_DEBUG", "").split(",")):
+            key, _, val = item.partition("=")
+            getattr(lib, "ds_debug_set_" + key.strip())(int(val))
         _lib = lib
         return lib
 
