@@ -181,3 +181,17 @@ def test_ip_adapter_processor_follows_the_reference_contract():
     assert float(same) == pytest.approx(1.0, abs=1e-5) and -1.0 <= float(s) < 1.0
     with pytest.raises(NotImplementedError):
         proc(attn, x, encoder_hidden_states=(text, [ip]), ip_adapter_masks=[torch.ones(1, 1, 16, 16, device=dev)])
+
+
+def test_cli_drivers_run_end_to_end(tmp_path, capsys):
+    _cuda()
+    from diffsim_b200 import __main__ as cli
+
+    assert cli.main(["cute", "--similarity", "cosine", "--n", "6"]) == 0
+    out = capsys.readouterr().out
+    assert "Current total samples: 6" in out and "CUTE accuracy: 100.00%" in out     # positives are far closer than negatives
+    assert cli.main(["nights", "--similarity", "mse", "--n", "5"]) == 0
+    assert "Final validation accuracy: 100.00%" in capsys.readouterr().out
+    assert cli.main(["sref", "--similarity", "cosine", "--n", "3", "--out_path", str(tmp_path)]) == 0
+    out = capsys.readouterr().out
+    assert "precision@3: 100.00%" in out and (tmp_path / "001" / "2.txt").exists()

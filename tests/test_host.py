@@ -102,3 +102,13 @@ def test_hostbind_parses_sysfs_lists_and_never_raises():
     assert hostbind._parse_cpulist("") == []
     r = hostbind.bind_to_gpu_node(0)          # no GPU here: the affinity is left alone, with the reason stated
     assert r["bound"] is False and isinstance(r["why"], str)
+
+
+def test_cli_keeps_reference_flags_and_launcher_presets():
+    from diffsim_b200 import __main__ as cli
+
+    a = cli.build_parser().parse_args(["nights", "--similarity", "cosine", "--seed", "2334"])
+    assert cli.resolve(a) == {"target_block": "up_blocks", "target_layer": [0], "target_step": 500}   # night_main.sh
+    a = cli.build_parser().parse_args(["cute", "--target_step", "750", "--target_layer", "3", "--target_block", "down_blocks"])
+    assert cli.resolve(a) == {"target_block": "down_blocks", "target_layer": [3], "target_step": 750}   # explicit flags win
+    assert a.similarity == "mse" and a.metric == "diffsim"                                            # reference defaults
