@@ -77,7 +77,7 @@ def main(argv=None) -> int:
     rows = []
     for t in range(args.n):
         a_pos = 0.55 + 0.4 * float(torch.rand((), generator=g))
-        a_neg = 0.15 + 0.4 * float(torch.rand((), generator=g))
+        a_neg = 0.15 + 0.3 * float(torch.rand((), generator=g))
         ref, pos, neg = f"c{t}@1.0", f"c{t}@{a_pos:.3f}", f"c{t}@{a_neg:.3f}"
         if args.benchmark == "nights":
             left_is_pos = bool(torch.rand((), generator=g) < 0.5)
