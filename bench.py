@@ -36,7 +36,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SHAPE = (2, 8, 256, 160)  # SD-1.5 512^2 up_blocks layer 0
-DRAM_BYTES_PER_TRIPLET = (8.900047e9 + 10.940672e6) / 512  # ncu --set full, profiles/r1w_attn_ncu_summary.txt
+DRAM_BYTES_PER_TRIPLET = (8.687563e9 + 8.980992e6) / 512  # ncu --set full, profiles/r1final_attn_ncu_summary.txt
 WORKLOAD = "nights_2afc_triplets_sd15_512_up0_cosine"
 METRIC = "scored_pairs_per_sec"
 
