@@ -85,6 +85,36 @@ static int gemm_sym_tile_count(int tiles_m, int tiles_n, int bm = kGBM) {
   return n;
 }
 
+// 64 accumulator columns of this thread's row: TMEM -> (+ bias) -> 32 packed 16-bit pairs (128 bytes)
+template <bool kBf16>
+__device__ __forceinline__ void gemm_load_row64(const GemmParams& p, uint32_t t_addr, int col0, uint32_t (&w)[32]) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t v[32];
+    tmem_ld_x32(t_addr + half * 32, v);
+    tmem_wait_ld();
+    const int cb = col0 + half * 32;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+      if (p.bias && cb + g * 8 < p.N) {
+        const uint4 b4 = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.bias) + cb + g * 8));
+        const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 bf = unpack2<kBf16>(bw[j]);
+          f[2 * j] += bf.x;
+          f[2 * j + 1] += bf.y;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[half * 16 + g * 4 + j] = pack2<kBf16>(f[2 * j], f[2 * j + 1]);
+    }
+  }
+}
+
 // Epilogue of one warp: its 32 accumulator rows (TMEM lanes) across the kGBN columns of the tile, 128 bytes of a row per
 // pass (32 fp32 partials or 64 16-bit outputs).  A thread owns a ROW in TMEM, so storing straight from registers makes every
 // warp-wide 16-byte store touch 32 different 128-byte lines (measured: the projection runs at 1166 TFLOP/s with such stores
@@ -107,31 +137,7 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, uint32_t
       tmem_ld_x32(t_addr + ps * 32, w);
       tmem_wait_ld();
     } else {
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t v[32];
-        tmem_ld_x32(t_addr + ps * 64 + half * 32, v);
-        tmem_wait_ld();
-        const int cb = col0 + half * 32;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float f[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-          if (p.bias && cb + g * 8 < p.N) {
-            const uint4 b4 = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.bias) + cb + g * 8));
-            const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 bf = unpack2<kBf16>(bw[j]);
-              f[2 * j] += bf.x;
-              f[2 * j + 1] += bf.y;
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) w[half * 16 + g * 4 + j] = pack2<kBf16>(f[2 * j], f[2 * j + 1]);
-        }
-      }
+      gemm_load_row64<kBf16>(p, t_addr + ps * 64, col0, w);
     }
     // registers (thread = row) -> staging patch
 #pragma unroll
@@ -314,31 +320,7 @@ __device__ __forceinline__ void gemm_epilogue_rows_tma(const GemmParams& p, cons
     if (lane == 0) tma_store_wait_read<1>();
     __syncwarp();
     uint32_t w[32];
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t v[32];
-      tmem_ld_x32(t_addr + ps * 64 + half * 32, v);
-      tmem_wait_ld();
-      const int cb = col0 + half * 32;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        float f[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-        if (p.bias && cb + g * 8 < p.N) {
-          const uint4 b4 = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.bias) + cb + g * 8));
-          const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 bf = unpack2<kBf16>(bw[j]);
-            f[2 * j] += bf.x;
-            f[2 * j + 1] += bf.y;
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) w[half * 16 + g * 4 + j] = pack2<kBf16>(f[2 * j], f[2 * j + 1]);
-      }
-    }
+    gemm_load_row64<kBf16>(p, t_addr + ps * 64, col0, w);
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const uint32_t a = st_base + (uint32_t)lane * 128u + (uint32_t)((u ^ (lane & 7)) << 4);
