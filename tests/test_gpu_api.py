@@ -195,3 +195,29 @@ def test_cli_drivers_run_end_to_end(tmp_path, capsys):
     assert cli.main(["sref", "--similarity", "cosine", "--n", "3", "--out_path", str(tmp_path)]) == 0
     out = capsys.readouterr().out
     assert "precision@3: 100.00%" in out and (tmp_path / "001" / "2.txt").exists()
+
+
+def test_torch_custom_ops_equal_the_direct_bindings():
+    dev = _cuda()
+    from diffsim_b200 import ops, synth, torch_ops  # noqa: F401  (registers torch.ops.diffsim_b200.*)
+
+    T = torch.ops.diffsim_b200
+    q, k, v = synth.device_cache(2, 4, 128, 64, 6, torch.float16, dev, seed=5)
+    pairs = torch.tensor([(0, 1), (2, 3), (4, 5)], dtype=torch.int32, device=dev)
+    assert torch.equal(T.aas_pairs(q, k, v, pairs, "cosine"), ops.aas_pairs(q, k, v, pairs, "cosine"))
+    assert torch.equal(T.aas_pairs(q, k, v, pairs, "mse", 0.1), ops.aas_pairs(q, k, v, pairs, "mse", 0.1))
+    assert torch.equal(T.attn_fwd(q[0], k[1], v[1]), ops.attn_fwd(q[0], k[1], v[1]))
+    s = T.aas_score(q[0], k[0], v[0], q[1], k[1], v[1], "cosine")
+    assert torch.equal(s, ops.aas_pairs(q, k, v, pairs[:1], "cosine"))
+    ab, ac, counts, flags = T.aas_triplets(q, k, v, torch.tensor([[0, 1, 2], [3, 4, 5]], dtype=torch.int32, device=dev))
+    assert torch.equal(ab, ops.aas_pairs(q, k, v, torch.tensor([(0, 1), (3, 4)]), "cosine")) and counts.shape == (2,)
+    assert torch.equal(T.aas_matrix(q, k, v, k, v), ops.aas_matrix(q, k, v, k, v))
+    x = q[0].reshape(1, -1)
+    y = q[1].reshape(1, -1)
+    assert torch.equal(T.pair_reduce(x, y, "minmax_cosine"), ops.pair_reduce(x, y, "minmax_cosine"))
+    f = torch.randn(40, 256, device=dev).half()
+    assert torch.equal(T.simmat(f), ops.simmat(f)) and torch.equal(T.simmat(f, f[:8]), ops.simmat(f, f[:8]))
+    h = torch.randn(64, 128, device=dev).half()
+    w = torch.randn(3 * 128, 128, device=dev).half()
+    outs = T.qkv_project(h, w, None, 3)
+    assert len(outs) == 3 and all(torch.equal(a, b) for a, b in zip(outs, ops.qkv_project(h, w, None, 3)))

@@ -112,3 +112,18 @@ def test_cli_keeps_reference_flags_and_launcher_presets():
     a = cli.build_parser().parse_args(["cute", "--target_step", "750", "--target_layer", "3", "--target_block", "down_blocks"])
     assert cli.resolve(a) == {"target_block": "down_blocks", "target_layer": [3], "target_step": 750}   # explicit flags win
     assert a.similarity == "mse" and a.metric == "diffsim"                                            # reference defaults
+
+
+def test_torch_custom_ops_are_registered_and_have_no_cpu_fallback():
+    import torch as _t
+
+    from diffsim_b200 import torch_ops
+
+    for name in torch_ops.OPERATORS:
+        assert hasattr(_t.ops.diffsim_b200, name)
+    x = _t.randn(2, 64).half()
+    with pytest.raises(NotImplementedError):          # the dispatcher has no CPU kernel to fall back to
+        _t.ops.diffsim_b200.pair_reduce(x, x, "cosine")
+    q = _t.randn(1, 2, 64, 64).half()
+    with pytest.raises(NotImplementedError):
+        _t.ops.diffsim_b200.attn_fwd(q, q, q)
