@@ -94,3 +94,21 @@ def run_nights(scorer, rows: Sequence[Tuple[Hashable, Hashable, Hashable, int]],
 def format_report(name: str, r: TwoAFCResult) -> List[str]:
     """The lines the reference drivers print at the end of a run."""
     return [f"Current total samples: {r.total}", f"{name} accuracy: {r.accuracy:.2f}%", f"{name} 2x accuracy: {r.accuracy_2x:.2f}%"]
+
+
+def ensemble_votes(metric_scores: Sequence[Tuple[torch.Tensor, torch.Tensor]], votes: Optional[torch.Tensor] = None) -> int:
+    """The reference's 'ensemble' metric: per triplet each member metric votes `0 if ab < ac else 1` -- ties count FOR the
+    positive, unlike the strict single-metric rule -- and the triplet is correct when at least two of the three agree
+    (cute_main.py:187-195); on NIGHTS the majority is compared with the annotators' vote: correct when (vote == 1 and
+    sum >= 2) or (vote == 0 and sum <= 1) (night_main.py:148-152).  metric_scores: [(ab, ac)] per member metric, each a
+    [T] tensor.  Returns the number of correct triplets (one device sync)."""
+    if len(metric_scores) != 3:
+        raise ValueError("the reference's ensemble has exactly three members (diffsim, clip_i, dino)")
+    total = None
+    for ab, ac in metric_scores:
+        corr = (~(ab < ac)).to(torch.int32)
+        total = corr if total is None else total + corr.to(total.device)
+    if votes is None:
+        return int((total >= 2).sum())
+    votes = votes.to(total.device)
+    return int((((votes == 1) & (total >= 2)) | ((votes == 0) & (total <= 1))).sum())

@@ -170,3 +170,19 @@ def test_drivers_extract_each_image_once_and_decide_like_the_reference(monkeypat
     # mse flips the comparison (cute_main.py:196-200)
     rm = drivers.run_2afc(sc, trips, similarity="mse", device="cpu")
     assert rm.flags.tolist() == [1, 0, 1]
+
+
+def test_ensemble_majority_vote_rules():
+    """cute_main.py:187-195 and night_main.py:148-152: ties vote for the positive; two of three decide."""
+    from diffsim_b200 import drivers
+
+    t = torch.tensor
+    diff = (t([0.9, 0.2, 0.5, 0.1]), t([0.1, 0.8, 0.5, 0.3]))     # votes 1, 0, 1 (tie), 0
+    clip = (t([0.7, 0.9, 0.1, 0.2]), t([0.6, 0.1, 0.9, 0.9]))     # votes 1, 1, 0, 0
+    dino = (t([0.1, 0.1, 0.4, 0.9]), t([0.5, 0.5, 0.3, 0.1]))     # votes 0, 0, 1, 1
+    # sums: 2, 1, 2, 1 -> correct: yes, no, yes, no
+    assert drivers.ensemble_votes([diff, clip, dino]) == 2
+    # NIGHTS: vote 1 needs sum >= 2, vote 0 needs sum <= 1
+    assert drivers.ensemble_votes([diff, clip, dino], votes=t([1, 0, 0, 1])) == 2
+    with pytest.raises(ValueError):
+        drivers.ensemble_votes([diff, clip])
