@@ -214,7 +214,7 @@ class DiffSim:
     """SD-1.5 scorer -- diffsim/diffsim.py:80-258."""
 
     def __init__(self, torch_dtype=torch.float16, device="cuda", ip_adapter=False, trunk: Optional[Trunk] = None,
-                 match_reference_dtype: bool = True, compat_layer_collapse: bool = True):
+                 match_reference_dtype: bool = True, compat_layer_collapse: bool = True, compat_value_slices: bool = True):
         # ip_adapter=True: the trunk must provide extract_ip() (query + per-adapter ip keys / values).  In the reference
         # the hook that should capture them cannot fire (attn2 receives encoder_hidden_states as a keyword, SURVEY.md
         # section 5); the scoring arithmetic of diffsim/diffsim.py:172-175,184-185 is implemented regardless.
@@ -222,6 +222,7 @@ class DiffSim:
         self.trunk = trunk if trunk is not None else SyntheticTrunk(dtype=torch_dtype, device=device)
         self.match_reference_dtype = match_reference_dtype
         self.compat_layer_collapse = compat_layer_collapse
+        self.compat_value_slices = compat_value_slices
 
     def diffsim(self, image_A, image_B, img_size, prompt, target_block, target_layer, target_step, ip_adapter=False,
                 seed="2333", device="cuda", similarity="cosine"):
@@ -237,11 +238,27 @@ class DiffSim:
         B = self.trunk.extract(image_B, img_size, prompt, target_block, layer, target_step, generator)
         return aas_score(A, B, similarity, None, self.match_reference_dtype)
 
-    def diffsim_value(self, image_A, img_size, prompt, target_block, target_layer, target_step, ip_adapter=False,
-                      seed="2333", device="cuda", similarity="cosine"):
+    def extract(self, image, img_size, prompt, target_block, target_layer, target_step, seed="2333", device="cuda"):
+        """(q, k, v) of one image exactly as diffsim() captures them -- same layer indexing -- which is what a cache for
+        batched scoring must hold (drivers.build_cache)."""
         layer = resolve_sd15_layer(target_layer, self.compat_layer_collapse)
         generator = get_generator(seed, "cpu" if isinstance(self.trunk, SyntheticTrunk) else device)
-        return self.trunk.extract(image_A, img_size, prompt, target_block, layer, target_step, generator)
+        return self.trunk.extract(image, img_size, prompt, target_block, layer, target_step, generator)
+
+    def diffsim_value(self, image_A, img_size, prompt, target_block, target_layer, target_step, ip_adapter=False,
+                      seed="2333", device="cuda", similarity="cosine"):
+        """diffsim/diffsim.py:201-258.  The reference indexes the blocks differently here than in diffsim()
+        (down_blocks[1:] / up_blocks[:-1] instead of down_blocks[:-1] / up_blocks[1:], :224-244 vs :125-145), so the same
+        --target_layer names another layer; a trunk that knows about it (DiffusersTrunk.value_mode) reproduces that when
+        compat_value_slices is set (default), else this is extract()."""
+        trunk = self.trunk
+        if self.compat_value_slices and getattr(trunk, "value_mode", None) is not None:
+            old, trunk.value_mode = trunk.value_mode, True
+            try:
+                return self.extract(image_A, img_size, prompt, target_block, target_layer, target_step, seed, device)
+            finally:
+                trunk.value_mode = old
+        return self.extract(image_A, img_size, prompt, target_block, target_layer, target_step, seed, device)
 
 
 class diffsim_xl:  # noqa: N801 (the reference's name)

@@ -3,7 +3,7 @@
 The reference walks a dataset, calls `DiffSim.diffsim` twice per triplet (extracting the reference image twice,
 cute_main.py:111-132) and synchronises with the device on every comparison (cute_main.py:196-205,
 night_main.py:157-163).  Here a driver
-  1. extracts every DISTINCT image once through the scorer's trunk (`diffsim_value`, diffsim/diffsim.py:201-258),
+  1. extracts every DISTINCT image once through the scorer's trunk (the per-image capture of diffsim/diffsim.py:122-169),
   2. stacks the (q,k,v) into a cache,
   3. scores all triplets with ONE library call (ds_aas_triplets: 7 attentions per triplet instead of 8, decisions and
      counts on the device) and reads the counts back once.
@@ -53,7 +53,9 @@ def build_cache(scorer, images: Sequence[Hashable], img_size, prompt, target_blo
         if im in index:
             continue
         index[im] = len(qkvs)
-        qkvs.append(scorer.diffsim_value(im, img_size, prompt, target_block, target_layer, target_step, seed=seed, device=device))
+        # extract() = the layer diffsim() scores (the reference's diffsim_value() indexes the blocks differently)
+        fn = getattr(scorer, "extract", None) or scorer.diffsim_value
+        qkvs.append(fn(im, img_size, prompt, target_block, target_layer, target_step, seed=seed, device=device))
     return QKVCache.from_images(qkvs, device), index
 
 

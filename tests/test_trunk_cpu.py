@@ -118,3 +118,22 @@ def test_extract_captures_qkv_stops_early_and_leaves_no_hook():
     with pytest.raises(IndexError):
         trunk.extract(img, 16, "a photo", "up_blocks", 3, 0, torch.Generator().manual_seed(1))   # up_blocks[1:] has 3 entries
     assert isinstance(hooks.StopForward(), Exception)
+
+
+def test_diffsim_value_reproduces_the_reference_slice_quirk_and_extract_does_not():
+    from diffsim_b200.diffsim import DiffSim
+
+    pipe = _Pipe()
+    ds = DiffSim(torch.float32, "cpu", trunk=DiffusersTrunk(pipe, "cpu", torch.float32))
+    img = Image.new("RGB", (8, 8), (1, 2, 3))
+    args = (img, 16, "p", "up_blocks", [0], 600)
+    u = pipe.unet
+    scored = u.up_blocks[1:][0].attentions[-1].transformer_blocks[-1].attn1       # diffsim/diffsim.py:143-145
+    quirky = u.up_blocks[:-1][0].attentions[-1].transformer_blocks[-1].attn1      # diffsim/diffsim.py:242-244
+    q, _, _ = ds.extract(*args, seed="2333", device="cpu")
+    assert scored.stores[0] is q and getattr(quirky, "stores", None) is None
+    qv, _, _ = ds.diffsim_value(*args, seed="2333", device="cpu")
+    assert quirky.stores[0] is qv and ds.trunk.value_mode is False                  # restored afterwards
+    ds2 = DiffSim(torch.float32, "cpu", trunk=DiffusersTrunk(_Pipe(), "cpu", torch.float32), compat_value_slices=False)
+    q2, _, _ = ds2.diffsim_value(*args, seed="2333", device="cpu")
+    assert ds2.trunk.pipe.unet.up_blocks[1].attentions[-1].transformer_blocks[-1].attn1.stores[0] is q2
