@@ -63,12 +63,6 @@ constexpr int kTmemOs = 416;     // O_self, packed 16-bit: [416, 416 + D_PAD/2)
 #ifndef DS_PV_UNROLL
 #define DS_PV_UNROLL 1
 #endif
-#ifndef DS_WARP_ARRIVE
-#define DS_WARP_ARRIVE 0     // 1: one elected lane per warp arrives on p_full / o_empty (16 / 8 arrivals instead of 512 / 256)
-#endif
-#ifndef DS_MMA_WAIT
-#define DS_MMA_WAIT 0        // waits of the MMA-issuing thread: 0 suspend hint, 1 try_wait without hint, 2 test_wait spin
-#endif
 #ifndef DS_POLY_STRIDE
 #define DS_POLY_STRIDE -1    // -1: per head dim (AttnCfg::POLY_STRIDE); >= 0 forces one value for every head dim (A/B builds)
 #endif
@@ -188,19 +182,6 @@ __device__ __forceinline__ void for_each_group(const AttnParams& p, F&& f) {
   }
 }
 
-// waits of the single MMA-issuing thread: it is the latency-critical serial resource of the pipeline, and one spinning
-// thread costs next to nothing in issue slots
-__device__ __forceinline__ void mma_wait(uint64_t* bar, uint32_t parity) {
-#if DS_MMA_WAIT == 0
-  mbar_wait(bar, parity);
-#else
-  uint32_t spins = 0;
-  while (!(DS_MMA_WAIT == 1 ? mbar_try_wait_nohint(bar, parity) : mbar_test_wait(bar, parity))) {
-    if (++spins == (1u << 28)) __trap();
-  }
-#endif
-}
-
 template <int D, bool kBf16, int MODE>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_ks,
@@ -245,11 +226,11 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     mbar_init(q_empty, 1);
     for (int h = 0; h < 2; ++h) {
       mbar_init(&s_full[h], 1);
-      mbar_init(&p_full[h], DS_WARP_ARRIVE ? 16 : 512);
+      mbar_init(&p_full[h], 512);
     }
     mbar_init(o_full, 1);
     mbar_init(pv_half, 1);
-    mbar_init(o_empty, DS_WARP_ARRIVE ? 8 : 256);
+    mbar_init(o_empty, 256);
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
@@ -348,10 +329,10 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         DS_TRACE_EV(10 + h);
         const uint32_t idesc_qk = umma_idesc_f16(fmt, kBlockQ, (uint32_t)((rows + 15) & ~15), 0, 0);
         if (h == 0 && G.first_of_stream) {
-          mma_wait(q_full, sc & 1);
+          mbar_wait(q_full, sc & 1);
           ++sc;
         }
-        mma_wait(&kv_full[stage], phase);
+        mbar_wait(&kv_full[stage], phase);
         DS_TRACE_EV(12 + h);
         tc_fence_after_sync();
         const uint64_t k_desc = k_desc0 + (uint64_t)((stage * C::STAGE_BYTES) >> 4);
@@ -372,10 +353,10 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       auto issue_pv = [&](const GroupInfo& G, int h) {
         const int rows = h ? G.rowsB : G.rowsA;
         DS_TRACE_EV(20 + h);
-        mma_wait(&p_full[h], (h ? pv_cntB : pv_cntA) & 1);
+        mbar_wait(&p_full[h], (h ? pv_cntB : pv_cntA) & 1);
         DS_TRACE_EV(22 + h);
-        if (h == 0 && G.first_of_item) mma_wait(o_empty, (items_pv & 1) ^ 1);
-        mma_wait(&kv_full[stage], phase);
+        if (h == 0 && G.first_of_item) mbar_wait(o_empty, (items_pv & 1) ^ 1);
+        mbar_wait(&kv_full[stage], phase);
         DS_TRACE_EV(24 + h);
         tc_fence_after_sync();
         const uint64_t v_desc = v_desc0 + (uint64_t)((stage * C::STAGE_BYTES) >> 4);
@@ -538,12 +519,7 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
         tmem_wait_st();
         tc_fence_before_sync();
-#if DS_WARP_ARRIVE
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[h]);
-#else
         mbar_arrive(&p_full[h]);
-#endif
         DS_TRACE_EV(38 + h);
         if (h) ++cntB; else ++cntA;
       }
@@ -606,12 +582,7 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           if (cross) tmem_ld_x8(os_col + (c + 1) * 8, os[cur ^ 1]);
         } else {
           tc_fence_before_sync();
-#if DS_WARP_ARRIVE
-          __syncwarp();
-          if (lane == 0) mbar_arrive(o_empty);
-#else
           mbar_arrive(o_empty);
-#endif
         }
         if constexpr (MODE == ATTN_MODE_STORE) {
           uint32_t pk[8];
