@@ -60,9 +60,6 @@ constexpr int kTmemS = 0;        // S_A: columns [0,128), S_B: [128,256); P of t
                                  // overwrites the first 16 of its own 32 S columns
 constexpr int kTmemO = 256;      // O: [256, 256 + D_PAD)
 constexpr int kTmemOs = 416;     // O_self, packed 16-bit: [416, 416 + D_PAD/2)
-#ifndef DS_PV_UNROLL
-#define DS_PV_UNROLL 1
-#endif
 #ifndef DS_POLY_STRIDE
 #define DS_POLY_STRIDE -1    // -1: per head dim (AttnCfg::POLY_STRIDE); >= 0 forces one value for every head dim (A/B builds)
 #endif
@@ -368,15 +365,12 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           umma_f16_ts(tmem_base + kTmemO, a_tmem, v_desc + (uint64_t)((ks * 16 * C::SUB_BYTES) >> 4), idesc_pv, acc);
           umma_f16_ts(tmem_base + kTmemL, a_tmem, ones_desc, idesc_l, acc);   // l += P . 1
         };
-#if DS_PV_UNROLL
         // full halves (the common case) with compile-time operand offsets: the rolled loop spends ~25 dependent
         // uniform-datapath instructions per step, about as long as the tensor core needs for the step itself
         if (ksteps == kHalfKV / 16) {
 #pragma unroll
           for (int ks = 0; ks < kHalfKV / 16; ++ks) pv_step(ks);
-        } else
-#endif
-        {
+        } else {
 #pragma unroll 1
           for (int ks = 0; ks < ksteps; ++ks) pv_step(ks);
         }
