@@ -363,3 +363,23 @@ def test_simmat_symmetric_schedule_equals_the_full_one(n, L):
     ref = O.simmat(f[:64].cpu(), f.cpu(), "cosine")
     got = ops.simmat(f, None, "cosine")[:64].double().cpu()
     assert (got - ref).abs().max().item() < 2e-4
+
+
+def test_experimental_pair_kernel_matches_the_default_kernel():
+    """aas_attn_pair_kernel (cta_group::2 form of K1, off by default) against the default kernel on SD-1.5 up0 pairs: the
+    same MMAs in the same order on the same operands -> bit-identical scores (the case verified at the end of round 1)."""
+    dev = _cuda()
+    from diffsim_b200 import _native as N, ops, synth
+
+    lib = N.load()
+    q, k, v = synth.device_cache(2, 8, 256, 160, 6, torch.float16, dev, seed=3)
+    pairs = torch.tensor([(0, 1), (2, 3), (4, 5)], dtype=torch.int32)
+    ref = ops.aas_pairs(q, k, v, pairs, "cosine")
+    torch.cuda.synchronize()
+    lib.ds_debug_set_attn_pair(1)
+    try:
+        got = ops.aas_pairs(q, k, v, pairs, "cosine")
+        torch.cuda.synchronize()
+    finally:
+        lib.ds_debug_set_attn_pair(0)
+    assert torch.equal(got, ref)
