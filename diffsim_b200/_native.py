@@ -52,7 +52,6 @@ PROTOTYPES = {
     "ds_profile_enable": (_i, [_i]),
     "ds_profile_collect": (_i, [C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "ds_debug_set_trace": (_i, [_vp, _i]),
-    "ds_debug_set_attn_pair": (_i, [_i]),
     "ds_debug_set_gemm_variant": (_i, [_i]),
     "ds_debug_set_simmat_max_kb": (_i, [_i]),
     "ds_attn_fwd": (_i, [Tensor4, Tensor4, Tensor4, _f, Tensor4, _vp, _sz, _vp]),

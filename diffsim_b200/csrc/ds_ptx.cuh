@@ -188,6 +188,16 @@ __device__ __forceinline__ void tc_fence_after_sync() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
+// Warpgroup register re-allocation (setmaxnreg works on aligned groups of four warps; every warp of the group executes it).
+template <int R>
+__device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R));
+}
+template <int R>
+__device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R));
+}
+
 // ---------------------------------------------------------------------------
 // tcgen05: MMA
 // ---------------------------------------------------------------------------

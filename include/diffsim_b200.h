@@ -89,10 +89,6 @@ int ds_profile_collect(float* total_ms, int* launches);
  * clocks CTA 0 spent in the last attention launch in word [8 x cap].  Returns 1 if tracing is compiled in, else 0.
  */
 int ds_debug_set_trace(void* dev_buf, int cap);
-/* EXPERIMENTAL, off by default: route K1 through aas_attn_pair_kernel, the cta_group::2 form (clusters of two CTAs on the
- * two q tiles of a (group, b, h); needs head dim 64 / 128 / 160, kv length % 256 == 0, query length % 256 == 0).  Verified
- * bit-identical to the default kernel on SD-1.5 up0 pairs at the end of round 1; not yet benchmarked. */
-int ds_debug_set_attn_pair(int on);
 /* Debug / A-B only: GEMM kernel behind ds_qkv_project and ds_simmat: -1 automatic (default), 0 the 1-CTA 128x256 kernel
  * only, 2 the CTA-pair (cta_group::2, 256x256) kernel always.  Adding 16 to 0 / 2 (or passing -17 for automatic) selects
  * the epilogue without TMA stores. */

@@ -22,11 +22,10 @@ ops.aas_pairs(q, k, v, pairs, "cosine")
 torch.cuda.synchronize()
 lib.ds_debug_set_trace(None, 0)
 t = buf.cpu().view(8, CAP)
-names = {1: "prod wait kv_empty", 2: "prod got slot", 10: "mma qkA begin", 11: "mma qkB begin", 12: "mma qkA kv ready", 13: "mma qkB kv ready",
-         14: "mma qkA issued", 15: "mma qkB issued", 20: "mma pvA begin", 21: "mma pvB begin", 22: "mma pvA p_full", 23: "mma pvB p_full",
-         24: "mma pvA kv ready", 25: "mma pvB kv ready", 26: "mma pvA issued", 27: "mma pvB issued",
-         30: "sm wait sA", 31: "sm wait sB", 32: "sm got sA", 33: "sm got sB", 34: "sm chunk0 loaded, m known A", 35: "sm chunk0 loaded, m known B", 60: "sm max+vote done", 61: "sm exp done", 62: "sm next chunk landed", 50: "sm chunk0 done", 51: "sm chunk1 done", 52: "sm chunk2 done", 53: "sm chunk3 done",
-         36: "sm bar passed A", 37: "sm bar passed B", 38: "sm arrived pA", 39: "sm arrived pB", 40: "epi o_full", 41: "epi done"}
+names = {1: "prod wait kv_empty", 2: "prod got slot", 10: "mma qk begin", 11: "mma qk s_free ok", 12: "mma qk kv ready", 13: "mma qk mmas issued", 14: "mma qk committed",
+         20: "mma pv begin", 22: "mma pv p_full ok", 23: "mma pv o_empty ok", 24: "mma pv kv ready", 25: "mma pv mmas issued", 26: "mma pv committed",
+         30: "sm wait s_full", 32: "sm got S", 34: "sm max written", 36: "sm bar passed", 38: "sm arrived p_full",
+         40: "epi o_full", 42: "epi released O", 41: "epi done"}
 ev = []
 for slot in range(8):
     for x in t[slot].tolist():
@@ -44,7 +43,7 @@ lo = int(os.environ.get("TR_LO", "60000")); hi = int(os.environ.get("TR_HI", "85
 last = {}
 for clk, slot, tag in ev:
     r = clk - t0
-    if lo <= r <= hi:
+    if lo <= r <= hi and (not os.environ.get("TR_SLOT") or str(slot) in os.environ["TR_SLOT"].split(",")):
         d = r - last.get(slot, r)
         print(f"{r:8d} (+{d:5d}) slot{slot} {names.get(tag, tag)}")
     last[slot] = r
