@@ -1,43 +1,43 @@
 // K1 -- fused cross-image attention + similarity epilogue (tensor-core bound).
 //
-// One persistent, warp-specialised CTA per SM, 28 warps = 7 warpgroups (register budgets are re-dealt per role with
-// setmaxnreg, which works on aligned groups of four warps):
+// One persistent, warp-specialised CTA per SM:
 //
-//   warp 26       TMA producer   Q tile (per stream) and a ring of 128-row K / V stages
-//   warp 27       MMA issuer     tcgen05.mma: S = Q K^T (fp32, TMEM), O (+)= P V (fp32, TMEM; P read from TMEM);
-//                                also allocates / frees TMEM.  (warps 24-25 idle: their registers go to the epilogue)
-//   warps 0-15    softmax        512 threads; thread = (q row, 32 of the 128 kv columns of a half-step);
-//                                S (TMEM) -> registers -> exp2 -> P (16-bit, TMEM, double-buffered: the A operand of PV)
-//   warps 16-23   epilogue       256 threads; thread = (q row, half of the head dim).  Copies its part of O into
-//                                registers and hands the accumulator straight back to the tensor core, then
+//   warp 0        TMA producer   Q tile (per stream) and a ring of 128-row K / V stages
+//   warp 1        MMA issuer     tcgen05.mma: S = Q K^T (fp32, TMEM), O (+)= P V (fp32, TMEM; P read from TMEM);
+//                                also allocates / frees TMEM
+//   warps 10-25   softmax        512 threads; thread = (q row, 32 of the 128 kv columns of an S half);
+//                                S (TMEM) -> exp2 -> P (16-bit, written IN PLACE over S: the A operand of PV)
+//   warps 2-9     epilogue       256 threads; thread = (q row, half of the head dim); O (TMEM) -> 1/l ->
 //                                  self item : O_self rounded to the input dtype, kept on chip (TMEM), |O_self|^2
 //                                  cross item: dot(O_cross,O_self), |O_cross|^2 or sum (O_cross-O_self)^2
 //                                  store mode: write O to global (the SDPA replacement)
 //
-// Work decomposition.  A "stream" is (group, b, h, 128-row q tile): the Q tile stays resident while the kv images of
-// the group ("items") stream through; the first item of a group is the query image's own K/V (the self attention of
-// diffsim/diffsim.py:179-180), whose output never leaves the SM.  An item is cut into HALF-STEPS of 128 kv rows = one
-// ring stage of K, one of V, one N = 128 MMA slice of S.
+// (O is single-buffered in TMEM -- 2 x 160 columns do not fit next to S -- so the time the epilogue needs to drain
+// it sits on the critical path of the next item's first PV: hence eight epilogue warps, two per scheduler.)
 //
-// Pipeline (round 2; the round-1 kernel kept two S halves with P written in place, one O and row sums on the tensor
-// core -- its in-kernel timeline showed the tensor pipe idle ~45% of an item: behind the epilogue draining the single O
-// accumulator, behind ~7 try_waits of the MMA thread per item, and behind 16 N = 16 row-sum MMAs that each cost a full
-// issue slot; profiles/r2b_attn_timeline.txt).  Now:
-//   * S is single-buffered but handed back EARLY: the softmax warps arrive on s_free as soon as S(h) sits in their
-//     registers, so S(h+1) = Q K(h+1)^T is computed while they are still turning S(h) into P(h).  The tensor pipe runs
-//     QK one half-step ahead: QK(0), QK(1), PV(0), QK(2), PV(1), ...  -- the softmax warps never wait for S.
-//   * P is a separate, double-buffered 64-column region (P(h) in buffer h & 1): PV(h) reads it while P(h+1) is written.
-//   * Row sums l are accumulated by the softmax threads (packed fp32 adds, FMA pipe) and passed to the epilogue through
-//     shared memory: 36 MMAs per item instead of 52.
-//   * The epilogue warps own 112 registers each (setmaxnreg): they pull their 80 columns of O into registers in one
-//     go and release O (o_empty) before doing any arithmetic; the drain is ~300 clocks and hides under the QK that is
-//     already queued.
+// Work decomposition.  A "stream" is (group, b, h, 128-row q tile): the Q tile stays resident while the kv
+// images of the group ("items") stream through; the first item of a group is the query image's own K/V (the
+// self attention of diffsim/diffsim.py:179-180), whose output never leaves the SM.  An item is cut into kv
+// GROUPS of 256 rows, a group into two HALVES (A, B) of 128 rows = one ring stage = one N=128 MMA slice with
+// its own 128 TMEM columns.
 //
-// Softmax.  Online over 128-column half-steps with a LAZY running maximum: the first half-step of an item fixes the
-// reference maximum m of every row; a later one only moves m (and rescales O and the running sums) when some row
-// exceeds m by more than 2^14 (fp16 P) / 2^30 (bf16 P) -- otherwise p = exp2(s - m) is simply allowed to be large, which
-// 16-bit P and fp32 sums hold without loss.  The result is the exact softmax either way (any common offset cancels in
-// O / l).
+// Why this shape: the kernel is bound by shared-memory bandwidth (128 B/clk/SM), not by the tensor pipe, as
+// soon as operands are re-read from shared memory: an SS-mode MMA with N=64 reads 6 KB per 32 tensor-clocks.
+// So S is produced by N=128 MMAs (Q is re-read only twice per item), P never touches shared memory (the
+// softmax warps overwrite S in TMEM with 16-bit P and the PV MMA takes its A operand from TMEM), and O_self
+// lives in TMEM as well.  Shared memory then carries only TMA writes + one read of K and V + two reads of Q.
+//
+// Softmax.  Online over 128-column halves with a LAZY running maximum: the first half of an item fixes the
+// reference maximum m of every row; a later half only moves m (and rescales O and the running sum) when some
+// row of the tile exceeds m by more than 2^8 -- otherwise p = exp2(s - m) is simply allowed to be as large as
+// 256, which 16-bit P and fp32 sums hold without loss.  The result is the exact softmax either way (any common
+// offset cancels in O / l).  The rare rescale is done by the first-quarter softmax warps themselves before they
+// release P, so the common path has no extra barrier and half A never waits for half B.
+//
+// Pipeline.  The MMA warp issues, in this fixed order, PV_A(u), QK_A(u+1), PV_B(u), QK_B(u+1): tcgen05 ops of
+// one thread execute in issue order, so QK_A(u+1) may overwrite the columns PV_A(u) reads P from without any
+// barrier; while the tensor core works on half A the softmax warps turn half B into P.  The TMA producer feeds
+// the ring in the same order.
 //
 // Replaces diffsim/diffsim.py:177-197 (diffsim_xl.py:135-155, diffsim_dit.py:130-142).
 // Algorithmic work per directional attention: 4*B*H*Sq*Skv*D flops.
@@ -48,35 +48,30 @@ namespace ds {
 
 enum : int { ATTN_MODE_COS = 0, ATTN_MODE_MSE = 1, ATTN_MODE_STORE = 2 };
 
-constexpr int kAttnThreads = 896;   // 28 warps: 16 softmax | 8 epilogue | 2 idle, producer, MMA
-// The warp scheduler favours the HIGHEST warp id among the eligible warps of a sub-partition: the MMA issuer and the TMA
-// producer sit on top (their instruction streams are short but every one of their stalls idles the tensor pipe), the
-// epilogue (which holds the O accumulator hostage) next, the throughput-bound softmax warps at the bottom.
-constexpr int kWarpSoftmax0 = 0;
-constexpr int kWarpEpi0 = 16;
-constexpr int kWarpCtl0 = 24;       // warpgroup 6: warps 24, 25 idle
-constexpr int kWarpProducer = 26;
-constexpr int kWarpMma = 27;
-constexpr int kRegsCtl = 40;        // warpgroup 6 (producer / MMA / idle)
-constexpr int kRegsSoftmax = 64;
-constexpr int kRegsEpi = 104;       // 128 * 40 + 512 * 64 + 256 * 104 = 64512 = 896 * 72 (what the kernel is launched with)
+constexpr int kAttnThreads = 832;   // 26 warps: producer, MMA, 8 epilogue, 16 softmax
+constexpr int kWarpProducer = 0;
+constexpr int kWarpMma = 1;
+constexpr int kWarpSoftmax0 = 10;
 constexpr int kBlockQ = 128;     // q rows per tile == TMEM lanes
-constexpr int kHalfKV = 128;     // kv rows per half-step == per ring stage
+constexpr int kHalfKV = 128;     // kv rows per S half == per ring stage
+constexpr int kGroupKV = 256;    // kv rows per softmax group (two halves)
 constexpr int kTmemCols = 512;
-constexpr int kTmemO = 0;        // O: [0, D_PAD)
-constexpr int kTmemOs = 160;     // O_self, packed 16-bit: [160, 160 + D_PAD/2)
-constexpr int kTmemS = 256;      // S: [256, 384)
-constexpr int kTmemP = 384;      // P(h & 1): [384 + 64 (h & 1), +64): the thread's 32 kv columns -> 16 packed columns
+constexpr int kTmemS = 0;        // S_A: columns [0,128), S_B: [128,256); P of the thread's 32 kv columns
+                                 // overwrites the first 16 of its own 32 S columns
+constexpr int kTmemO = 256;      // O: [256, 256 + D_PAD)
+constexpr int kTmemOs = 416;     // O_self, packed 16-bit: [416, 416 + D_PAD/2)
 #ifndef DS_POLY_STRIDE
 #define DS_POLY_STRIDE -1    // -1: per head dim (AttnCfg::POLY_STRIDE); >= 0 forces one value for every head dim (A/B builds)
 #endif
+constexpr int kTmemL = 496;      // softmax denominators l = P . 1 (a 16-column MMA against a constant ones tile): [496,512)
 
 template <int D>
 struct AttnCfg {
   static constexpr int D_PAD = (D + 15) / 16 * 16;
   // Every POLY_STRIDE-th pair of exponentials is evaluated with a degree-3 polynomial on the FMA pipe instead of MUFU
   // (0: none).  With head dims <= 80 an item carries at most half the tensor work of D = 160 but the same 32 768
-  // exponentials, and long-kv streams of such items are MUFU-bound.
+  // exponentials, and long-kv streams of such items are MUFU-bound: measured +13% on SDXL (2,20,1024,64) / (2,10,4096,64),
+  // +6% on SD-1.5 up1 / up2, neutral on DiT-XL/2, and -4% at D = 160 (profiles/r1z_poly_shapes.txt).
   static constexpr int POLY_STRIDE = DS_POLY_STRIDE >= 0 ? DS_POLY_STRIDE : (D <= 80 ? 3 : 0);
   static constexpr int SUBW = (D % 64 == 0) ? 64 : 32;           // elements per swizzle row
   static constexpr int SUB_BYTES = SUBW * 2;                      // 128 or 64: TMA box row == swizzle span
@@ -87,13 +82,13 @@ struct AttnCfg {
   static constexpr int Q_BYTES = NSUB * Q_SUB_BYTES;
   static constexpr int KV_SUB_BYTES = kHalfKV * SUB_BYTES;
   static constexpr int STAGE_BYTES = NSUB * KV_SUB_BYTES;
-  static constexpr int MISC_BYTES = 4096 /*max exchange*/ + 8192 /*row sums, 4 item slots*/ + 128 /*epilogue reduce*/ + 512 /*barriers*/;
+  static constexpr int MISC_BYTES = 2048 /*ones tile*/ + 4096 /*max exchange*/ + 128 /*epilogue reduce*/ + 512 /*barriers*/;
   static constexpr int kMaxSmem = 232448;
   static constexpr int STAGES_RAW = (kMaxSmem - Q_BYTES - MISC_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 12 ? 12 : STAGES_RAW;
   static constexpr int SMEM_BYTES = Q_BYTES + STAGES * STAGE_BYTES + MISC_BYTES;
   static_assert(STAGES >= 4, "not enough shared memory for the K/V ring");
-  static_assert(kTmemO + D_PAD <= kTmemOs && kTmemOs + D_PAD / 2 <= kTmemS, "TMEM budget");
+  static_assert(kTmemO + D_PAD <= kTmemOs && kTmemOs + D_PAD / 2 <= kTmemL, "TMEM budget");
   static_assert(Q_BYTES % 1024 == 0 && STAGE_BYTES % 1024 == 0, "swizzle atoms need 1024-byte aligned tiles");
 };
 
@@ -130,48 +125,29 @@ struct AttnParams {
 #define DS_TRACE_EV(tag)
 #endif
 
-// Wait accounting (-DDS_ACCT builds): per role, SM clocks spent inside each kind of wait / section, summed in registers and
-// written once at the end by CTA 0 into the trace buffer: word [slot * cap + i] = (count << 40 | clocks) of account i.
-#ifdef DS_ACCT
-#define DS_ACCT_DECL uint32_t _ac_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, _ac_n[8] = {0, 0, 0, 0, 0, 0, 0, 0}; uint32_t _ac_0 = 0;
-#define DS_ACCT_BEGIN() _ac_0 = (uint32_t)clock()
-#define DS_ACCT_END(i) do { _ac_t[i] += (uint32_t)clock() - _ac_0; ++_ac_n[i]; } while (0)
-#define DS_ACCT_FLUSH(slot)                                                                                  \
-  do {                                                                                                       \
-    if (p.trace && blockIdx.x == 0)                                                                          \
-      for (int _i = 0; _i < 8; ++_i)                                                                         \
-        p.trace[(size_t)(slot) * p.trace_cap + _i] = ((unsigned long long)_ac_n[_i] << 40) | _ac_t[_i];      \
-  } while (0)
-#else
-#define DS_ACCT_DECL
-#define DS_ACCT_BEGIN()
-#define DS_ACCT_END(i)
-#define DS_ACCT_FLUSH(slot)
-#endif
-
-// One half-step (128 kv rows) of one item of one stream, as every warp role enumerates them (identically).
-struct HalfInfo {
+// One kv group of one item of one stream, as every warp role enumerates them (identically).
+struct GroupInfo {
   int b, h, qt, bh, qi;     // stream
   int img, entry;           // item: kv image, index into kv_idx / part (cross items)
-  int kv0, rows;            // half-step: first kv row, valid rows (1..128)
+  int kv0, rowsA, rowsB;    // group: first kv row, valid rows of the two halves
   bool self, first_of_stream, last_of_stream, first_of_item, last_of_item;
 };
 
 template <typename F>
-__device__ __forceinline__ void for_each_half(const AttnParams& p, F&& f) {
+__device__ __forceinline__ void for_each_group(const AttnParams& p, F&& f) {
   const uint32_t BH = (uint32_t)(p.B * p.H);
   const uint32_t n_streams = (uint32_t)p.n_groups * BH * (uint32_t)p.n_qt;   // < 2^31, checked by the host
-  const int n_hs = (p.Skv + kHalfKV - 1) / kHalfKV;
+  const int n_grp = (p.Skv + kGroupKV - 1) / kGroupKV;
   // stream -> (bh, group, q tile): q tile fastest so that neighbouring CTAs share K/V in L2.  32-bit arithmetic only:
   // this decode sits between two items on every role's critical path.
   for (uint32_t st = blockIdx.x; st < n_streams; st += gridDim.x) {
-    HalfInfo X;
+    GroupInfo G;
     const uint32_t r = st / (uint32_t)p.n_qt;
-    X.qt = (int)(st - r * (uint32_t)p.n_qt);
-    X.bh = (int)(r / (uint32_t)p.n_groups);
-    const int g = (int)(r - (uint32_t)X.bh * (uint32_t)p.n_groups);
-    X.b = X.bh / p.H;
-    X.h = X.bh - X.b * p.H;
+    G.qt = (int)(st - r * (uint32_t)p.n_qt);
+    G.bh = (int)(r / (uint32_t)p.n_groups);
+    const int g = (int)(r - (uint32_t)G.bh * (uint32_t)p.n_groups);
+    G.b = G.bh / p.H;
+    G.h = G.bh - G.b * p.H;
     // the work list lives in global memory and every role walks it between barriers the compiler cannot move loads
     // across: pull the entries of the NEXT stream / item into L1 now so that the dependent loads below hit
     if (st + gridDim.x < n_streams) {
@@ -180,22 +156,69 @@ __device__ __forceinline__ void for_each_half(const AttnParams& p, F&& f) {
       prefetch_l1(p.group_q + g_n);
       prefetch_l1(p.group_off + g_n);
     }
-    X.qi = p.group_q[g];
+    G.qi = p.group_q[g];
     const int t0 = p.group_off[g], t1 = p.group_off[g + 1];
     const int n_items = (t1 - t0) + p.self_first;
     for (int it = 0; it < n_items; ++it) {
-      X.self = p.self_first && it == 0;
-      X.entry = t0 + it - p.self_first;
-      if (it + 1 < n_items) prefetch_l1(p.kv_idx + X.entry + 1);
-      X.img = X.self ? X.qi : p.kv_idx[X.entry];
-      for (int hh = 0; hh < n_hs; ++hh) {
-        X.kv0 = hh * kHalfKV;
-        X.rows = min(p.Skv - X.kv0, kHalfKV);
-        X.first_of_item = hh == 0;
-        X.last_of_item = hh == n_hs - 1;
-        X.first_of_stream = it == 0 && hh == 0;
-        X.last_of_stream = it == n_items - 1 && hh == n_hs - 1;
-        f(X);
+      G.self = p.self_first && it == 0;
+      G.entry = t0 + it - p.self_first;
+      if (it + 1 < n_items) prefetch_l1(p.kv_idx + G.entry + 1);
+      G.img = G.self ? G.qi : p.kv_idx[G.entry];
+      for (int gg = 0; gg < n_grp; ++gg) {
+        G.kv0 = gg * kGroupKV;
+        const int rem = p.Skv - G.kv0;
+        G.rowsA = min(rem, kHalfKV);
+        G.rowsB = max(0, min(rem - kHalfKV, kHalfKV));
+        G.first_of_item = gg == 0;
+        G.last_of_item = gg == n_grp - 1;
+        G.first_of_stream = it == 0 && gg == 0;
+        G.last_of_stream = it == n_items - 1 && gg == n_grp - 1;
+        f(G);
+      }
+    }
+  }
+}
+
+// Light-weight enumeration for the roles that only need the SHAPE of the work (MMA issuer, softmax warps): per kv group the
+// valid rows of its two halves and the first / last flags.  No divisions per stream -- (q tile, group) advance incrementally
+// -- and one pair of (L1-prefetched) loads per stream for the group's item count.
+struct LiteGroup {
+  int rowsA, rowsB;
+  bool first_of_stream, last_of_stream, first_of_item, last_of_item;
+};
+
+template <typename F>
+__device__ __forceinline__ void for_each_group_lite(const AttnParams& p, F&& f) {
+  const uint32_t nq = (uint32_t)p.n_qt, ng = (uint32_t)p.n_groups;
+  const uint32_t n_streams = ng * (uint32_t)(p.B * p.H) * nq;   // < 2^31, checked by the host
+  const int n_grp = (p.Skv + kGroupKV - 1) / kGroupKV;
+  const int rem_last = p.Skv - (n_grp - 1) * kGroupKV;
+  const int rowsA_last = min(rem_last, kHalfKV), rowsB_last = max(0, min(rem_last - kHalfKV, kHalfKV));
+  // stream st = (bh * n_groups + g) * n_qt + qt
+  uint32_t qt = blockIdx.x % nq, g = (blockIdx.x / nq) % ng;
+  const uint32_t d_qt = gridDim.x % nq, d_g = (gridDim.x / nq) % ng;
+  for (uint32_t st = blockIdx.x; st < n_streams; st += gridDim.x) {
+    const int n_items = p.group_off[g + 1] - p.group_off[g] + p.self_first;
+    qt += d_qt;
+    uint32_t carry = 0;
+    if (qt >= nq) {
+      qt -= nq;
+      carry = 1;
+    }
+    g += d_g + carry;
+    if (g >= ng) g -= ng;
+    prefetch_l1(p.group_off + g);
+    LiteGroup G;
+    for (int it = 0; it < n_items; ++it) {
+      for (int gg = 0; gg < n_grp; ++gg) {
+        const bool last = gg == n_grp - 1;
+        G.rowsA = last ? rowsA_last : kHalfKV;
+        G.rowsB = last ? rowsB_last : kHalfKV;
+        G.first_of_item = gg == 0;
+        G.last_of_item = last;
+        G.first_of_stream = it == 0 && gg == 0;
+        G.last_of_stream = it == n_items - 1 && last;
+        f(G);
       }
     }
   }
@@ -210,18 +233,17 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sRing = sQ + C::Q_BYTES;
-  float* sMax = reinterpret_cast<float*>(sRing + C::STAGES * C::STAGE_BYTES);  // [2 parity][4 col quarter][128]
-  float* sL = sMax + 1024;                                                     // [4 item slots][4 col quarter][128]
-  float* sRed = sL + 2048;                                                     // [2 parity][8 warps][2]
+  uint8_t* sOnes = sRing + C::STAGES * C::STAGE_BYTES;   // [16 rows][64] K-major tile: row 0 = 1.0, rows 1..15 = 0
+  float* sMax = reinterpret_cast<float*>(sOnes + 2048);  // [2 parity][4 col quarter][128]
+  float* sRed = sMax + 1024;                                                   // [2 parity][4 warps][4]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 32);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
-  uint64_t* s_full = bars + 2;      // S(h) written by the tensor core (one phase per half-step)
-  uint64_t* s_free = bars + 3;      // S(h) copied into the softmax warps' registers
-  uint64_t* p_full = bars + 4;      // [2] P(h) written into buffer h & 1
-  uint64_t* p_free = bars + 6;      // [2] PV(h) done: buffer h & 1 may be overwritten, O holds the contribution of half-step h
-  uint64_t* o_full = bars + 8;      // all PV of an item done: O complete (one phase per item)
-  uint64_t* o_empty = bars + 9;     // O copied into the epilogue warps' registers
+  uint64_t* s_full = bars + 2;      // [2] S half written by the tensor core
+  uint64_t* p_full = bars + 4;      // [2] P half written (over S) by the softmax warps
+  uint64_t* o_full = bars + 10;     // all PV of an item done: O complete (one phase per item)
+  uint64_t* pv_half = bars + 12;    // PV of one half done (one phase per half; only the rare rescale path waits on it)
+  uint64_t* o_empty = bars + 11;    // O read out by the epilogue warps
   uint64_t* kv_full = bars + 16;
   uint64_t* kv_empty = bars + 16 + C::STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16 + 2 * C::STAGES);
@@ -244,13 +266,12 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   if (warp == kWarpMma && lane == 0) {
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
-    mbar_init(s_full, 1);
-    mbar_init(s_free, 512);
     for (int h = 0; h < 2; ++h) {
+      mbar_init(&s_full[h], 1);
       mbar_init(&p_full[h], 512);
-      mbar_init(&p_free[h], 1);
     }
     mbar_init(o_full, 1);
+    mbar_init(pv_half, 1);
     mbar_init(o_empty, 256);
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
@@ -262,390 +283,351 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
+  // constant B operand of the row-sum MMA: l[r] = sum_k P[r,k] * 1.  Row 0 of a 128B-swizzled K-major tile is not
+  // permuted (its swizzle XOR is 0) and the other rows are all zero, so the fill is layout-trivial.
+  if (threadIdx.x < 512) {
+    const uint32_t one2 = kBf16 ? 0x3F803F80u : 0x3C003C00u;
+    reinterpret_cast<uint32_t*>(sOnes)[threadIdx.x] = threadIdx.x < 32 ? one2 : 0u;
+  }
+  fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= kWarpCtl0) {
-    reg_dealloc<kRegsCtl>();
-    if (warp == kWarpProducer) {
-      // ------------------------------------------------------------------ TMA producer
-      if (elect_one()) {
-        int stage = 0;
-        uint32_t phase = 0, sc = 0;
-        // one ring stage = up to 128 kv rows (rows past the tensor end are zero-filled by TMA)
-        DS_TRACE_DECL(0)
-        DS_ACCT_DECL
-        auto load_half = [&](const CUtensorMap* m, int img, int bb, int hh, int row0) {
-          DS_TRACE_EV(1);
-          DS_ACCT_BEGIN();
-          mbar_wait(&kv_empty[stage], phase ^ 1);
-          DS_ACCT_END(0);
-          DS_TRACE_EV(2);
-          uint8_t* dst = sRing + (size_t)stage * C::STAGE_BYTES;
-          mbar_arrive_expect_tx(&kv_full[stage], C::STAGE_BYTES);
+  if (warp == kWarpProducer) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0, sc = 0;
+      // one ring stage = up to 128 kv rows (rows past the tensor end are zero-filled by TMA)
+      DS_TRACE_DECL(0)
+      auto load_half = [&](const CUtensorMap* m, int img, int bb, int hh, int row0) {
+        DS_TRACE_EV(1);
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        DS_TRACE_EV(2);
+        uint8_t* dst = sRing + (size_t)stage * C::STAGE_BYTES;
+        mbar_arrive_expect_tx(&kv_full[stage], C::STAGE_BYTES);
+#pragma unroll
+        for (int s = 0; s < C::NSUB; ++s)
+          tma_load_5d(dst + s * C::KV_SUB_BYTES, m, &kv_full[stage], s * C::SUBW, row0, hh, bb, img);
+        if (++stage == C::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      GroupInfo prev = {};
+      bool have_prev = false;
+      for_each_group(p, [&](const GroupInfo& G) {
+        // the order the MMA warp consumes the ring in: V_A(u-1), K_A(u), V_B(u-1), K_B(u).  V_A(u-1) goes first, BEFORE
+        // the wait for the Q buffer: at a stream boundary that wait lasts until the old stream's last QK has completed,
+        // and PV_A(u-1) must not queue behind it.
+        if (have_prev) load_half(prev.self ? &map_vs : &map_v, prev.img, prev.b, prev.h, prev.kv0);
+        if (G.first_of_stream) {
+          mbar_wait(q_empty, (sc & 1) ^ 1);
+          mbar_arrive_expect_tx(q_full, C::Q_BYTES);
 #pragma unroll
           for (int s = 0; s < C::NSUB; ++s)
-            tma_load_5d(dst + s * C::KV_SUB_BYTES, m, &kv_full[stage], s * C::SUBW, row0, hh, bb, img);
-          if (++stage == C::STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
-        };
-        HalfInfo prev = {};
-        bool have_prev = false;
-        // the order the MMA warp consumes the ring in: K(h), V(h-1), K(h+1), V(h), ...
-        for_each_half(p, [&](const HalfInfo& X) {
-          if (X.first_of_stream) {
-            DS_ACCT_BEGIN();
-            mbar_wait(q_empty, (sc & 1) ^ 1);
-            DS_ACCT_END(1);
-            mbar_arrive_expect_tx(q_full, C::Q_BYTES);
-#pragma unroll
-            for (int s = 0; s < C::NSUB; ++s)
-              tma_load_5d(sQ + s * C::Q_SUB_BYTES, &map_q, q_full, s * C::SUBW, X.qt * kBlockQ, X.h, X.b, X.qi);
-            ++sc;
-          }
-          load_half(X.self ? &map_ks : &map_k, X.img, X.b, X.h, X.kv0);
-          if (have_prev) load_half(prev.self ? &map_vs : &map_v, prev.img, prev.b, prev.h, prev.kv0);
-          prev = X;
-          have_prev = true;
-        });
-        if (have_prev) load_half(prev.self ? &map_vs : &map_v, prev.img, prev.b, prev.h, prev.kv0);
-        DS_ACCT_FLUSH(0);
-      }
-    } else if (warp == kWarpMma) {
-      // ------------------------------------------------------------------ MMA issuer
-      if (elect_one()) {
-        const uint32_t fmt = kBf16 ? 1u : 0u;
-        const uint32_t idesc_pv = umma_idesc_f16(fmt, kBlockQ, C::D_PAD, 0, 1);
-        constexpr uint32_t SBO = 8 * C::SUB_BYTES;  // eight swizzle rows
-        // descriptors of the buffer bases; tiles are addressed by adding (byte offset >> 4) to the low word
-        const uint64_t q_desc0 = umma_smem_desc(smem_u32(sQ), 16, SBO, C::LAYOUT);
-        const uint64_t k_desc0 = umma_smem_desc(smem_u32(sRing), 16, SBO, C::LAYOUT);
-        const uint64_t v_desc0 = umma_smem_desc(smem_u32(sRing), C::KV_SUB_BYTES, SBO, C::LAYOUT);
-        int stage = 0;
-        uint32_t phase = 0;
-        uint32_t hq = 0, hp = 0, sc = 0, items_pv = 0;   // half-steps whose QK / PV have been issued
-        auto advance = [&]() {
-          if (++stage == C::STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
-        };
-        DS_TRACE_DECL(1)
-        DS_ACCT_DECL
-        // S = Q K^T of half-step hq: N = its kv rows rounded up to 16.  Needs S(hq - 1) to have left TMEM.
-        auto issue_qk = [&](const HalfInfo& X) {
-          DS_TRACE_EV(10);
-          const uint32_t idesc_qk = umma_idesc_f16(fmt, kBlockQ, (uint32_t)((X.rows + 15) & ~15), 0, 0);
-          if (X.first_of_stream) {
-            DS_ACCT_BEGIN();
-            mbar_wait(q_full, sc & 1);
-            DS_ACCT_END(0);
-            ++sc;
-          }
-          DS_ACCT_BEGIN();
-          if (hq > 0) mbar_wait(s_free, (hq - 1) & 1);
-          DS_ACCT_END(1);
-          DS_TRACE_EV(11);
-          DS_ACCT_BEGIN();
-          mbar_wait(&kv_full[stage], phase);
-          DS_ACCT_END(2);
-          DS_TRACE_EV(12);
-          DS_ACCT_BEGIN();
-          tc_fence_after_sync();
-          const uint64_t k_desc = k_desc0 + (uint64_t)((stage * C::STAGE_BYTES) >> 4);
-          const uint32_t d_tmem = tmem_base + kTmemS;
-#pragma unroll
-          for (int kc = 0; kc < C::D_PAD / 16; ++kc) {
-            const int sub = kc / C::CPS, off = (kc % C::CPS) * 32;
-            umma_f16_ss(d_tmem, q_desc0 + (uint64_t)((sub * C::Q_SUB_BYTES + off) >> 4),
-                        k_desc + (uint64_t)((sub * C::KV_SUB_BYTES + off) >> 4), idesc_qk, kc > 0 ? 1u : 0u);
-          }
-          DS_ACCT_END(3);
-          DS_TRACE_EV(13);
-          umma_commit(&kv_empty[stage]);
-          advance();
-          umma_commit(s_full);
-          DS_TRACE_EV(14);
-          if (X.last_of_stream) umma_commit(q_empty);
-          ++hq;
-        };
-        // O (+)= P V of half-step hp, P read from TMEM buffer hp & 1
-        auto issue_pv = [&](const HalfInfo& X) {
-          const uint32_t b = hp & 1;
-          DS_TRACE_EV(20);
-          DS_ACCT_BEGIN();
-          mbar_wait(&p_full[b], (hp >> 1) & 1);
-          DS_ACCT_END(4);
-          DS_TRACE_EV(22);
-          DS_ACCT_BEGIN();
-          if (X.first_of_item) mbar_wait(o_empty, (items_pv & 1) ^ 1);
-          DS_ACCT_END(5);
-          DS_TRACE_EV(23);
-          DS_ACCT_BEGIN();
-          mbar_wait(&kv_full[stage], phase);
-          DS_ACCT_END(6);
-          DS_TRACE_EV(24);
-          DS_ACCT_BEGIN();
-          tc_fence_after_sync();
-          const uint64_t v_desc = v_desc0 + (uint64_t)((stage * C::STAGE_BYTES) >> 4);
-          const uint32_t p_tmem = tmem_base + kTmemP + b * 64;
-          const int ksteps = (X.rows + 15) >> 4;
-          auto pv_step = [&](int ks) {
-            // A = P[:, 16 ks .. 16 ks + 15] = 8 packed TMEM columns
-            const uint32_t acc = (X.first_of_item && ks == 0) ? 0u : 1u;
-            umma_f16_ts(tmem_base + kTmemO, p_tmem + ks * 8, v_desc + (uint64_t)((ks * 16 * C::SUB_BYTES) >> 4), idesc_pv, acc);
-          };
-          // full half-steps (the common case) with compile-time operand offsets
-          if (ksteps == kHalfKV / 16) {
-#pragma unroll
-            for (int ks = 0; ks < kHalfKV / 16; ++ks) pv_step(ks);
-          } else {
-#pragma unroll 1
-            for (int ks = 0; ks < ksteps; ++ks) pv_step(ks);
-          }
-          DS_ACCT_END(7);
-          DS_TRACE_EV(25);
-          umma_commit(&kv_empty[stage]);
-          advance();
-          umma_commit(&p_free[b]);
-          DS_TRACE_EV(26);
-          if (X.last_of_item) {
-            umma_commit(o_full);
-            ++items_pv;
-          }
-          ++hp;
-        };
-        HalfInfo prev = {};
-        bool have_prev = false;
-        for_each_half(p, [&](const HalfInfo& X) {
-          issue_qk(X);
-          if (have_prev) issue_pv(prev);
-          prev = X;
-          have_prev = true;
-        });
-        if (have_prev) issue_pv(prev);
-        DS_ACCT_FLUSH(1);
+            tma_load_5d(sQ + s * C::Q_SUB_BYTES, &map_q, q_full, s * C::SUBW, G.qt * kBlockQ, G.h, G.b, G.qi);
+          ++sc;
+        }
+        load_half(G.self ? &map_ks : &map_k, G.img, G.b, G.h, G.kv0);
+        if (have_prev && prev.rowsB) load_half(prev.self ? &map_vs : &map_v, prev.img, prev.b, prev.h, prev.kv0 + kHalfKV);
+        if (G.rowsB) load_half(G.self ? &map_ks : &map_k, G.img, G.b, G.h, G.kv0 + kHalfKV);
+        prev = G;
+        have_prev = true;
+      });
+      if (have_prev) {
+        load_half(prev.self ? &map_vs : &map_v, prev.img, prev.b, prev.h, prev.kv0);
+        if (prev.rowsB) load_half(prev.self ? &map_vs : &map_v, prev.img, prev.b, prev.h, prev.kv0 + kHalfKV);
       }
     }
-  } else if (warp < kWarpEpi0) {
-    // ------------------------------------------------------------------ softmax (warps 0-15)
-    reg_dealloc<kRegsSoftmax>();
-    const int qtr = (warp - kWarpSoftmax0) >> 2;   // which 32 columns of the half-step
-    const int quad = warp & 3;                     // TMEM lane quadrant this warp may touch
+  } else if (warp == kWarpMma) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      const uint32_t fmt = kBf16 ? 1u : 0u;
+      const uint32_t idesc_pv = umma_idesc_f16(fmt, kBlockQ, C::D_PAD, 0, 1);
+      const uint32_t idesc_l = umma_idesc_f16(fmt, kBlockQ, 16, 0, 0);
+      const uint64_t ones_desc = umma_smem_desc(smem_u32(sOnes), 16, 1024, UMMA_SW128);
+      constexpr uint32_t SBO = 8 * C::SUB_BYTES;  // eight swizzle rows
+      // descriptors of the buffer bases; tiles are addressed by adding (byte offset >> 4) to the low word
+      const uint64_t q_desc0 = umma_smem_desc(smem_u32(sQ), 16, SBO, C::LAYOUT);
+      const uint64_t k_desc0 = umma_smem_desc(smem_u32(sRing), 16, SBO, C::LAYOUT);
+      const uint64_t v_desc0 = umma_smem_desc(smem_u32(sRing), C::KV_SUB_BYTES, SBO, C::LAYOUT);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t pv_cntA = 0, pv_cntB = 0, sc = 0, items_pv = 0;
+      auto advance = [&]() {
+        if (++stage == C::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      // S_h = Q K_h^T: N = the half's kv rows rounded up to 16.  Overwrites the columns PV_h of the previous group
+      // read P from: safe without a barrier because both are issued by this thread, in this order.
+      DS_TRACE_DECL(1)
+      auto issue_qk = [&](const LiteGroup& G, int h) {
+        const int rows = h ? G.rowsB : G.rowsA;
+        DS_TRACE_EV(10 + h);
+        const uint32_t idesc_qk = umma_idesc_f16(fmt, kBlockQ, (uint32_t)((rows + 15) & ~15), 0, 0);
+        if (h == 0 && G.first_of_stream) {
+          mbar_wait(q_full, sc & 1);
+          ++sc;
+        }
+        mbar_wait(&kv_full[stage], phase);
+        DS_TRACE_EV(12 + h);
+        tc_fence_after_sync();
+        const uint64_t k_desc = k_desc0 + (uint64_t)((stage * C::STAGE_BYTES) >> 4);
+        const uint32_t d_tmem = tmem_base + kTmemS + h * kHalfKV;
+#pragma unroll
+        for (int kc = 0; kc < C::D_PAD / 16; ++kc) {
+          const int sub = kc / C::CPS, off = (kc % C::CPS) * 32;
+          umma_f16_ss(d_tmem, q_desc0 + (uint64_t)((sub * C::Q_SUB_BYTES + off) >> 4),
+                      k_desc + (uint64_t)((sub * C::KV_SUB_BYTES + off) >> 4), idesc_qk, kc > 0 ? 1u : 0u);
+        }
+        umma_commit(&kv_empty[stage]);
+        advance();
+        umma_commit(&s_full[h]);
+        DS_TRACE_EV(14 + h);
+        if (G.last_of_stream && (h == 1 || G.rowsB == 0)) umma_commit(q_empty);
+      };
+      // O (+)= P_h V_h with P_h read from TMEM (written by the softmax warps over S_h)
+      auto issue_pv = [&](const LiteGroup& G, int h) {
+        const int rows = h ? G.rowsB : G.rowsA;
+        DS_TRACE_EV(20 + h);
+        mbar_wait(&p_full[h], (h ? pv_cntB : pv_cntA) & 1);
+        DS_TRACE_EV(22 + h);
+        if (h == 0 && G.first_of_item) mbar_wait(o_empty, (items_pv & 1) ^ 1);
+        mbar_wait(&kv_full[stage], phase);
+        DS_TRACE_EV(24 + h);
+        tc_fence_after_sync();
+        const uint64_t v_desc = v_desc0 + (uint64_t)((stage * C::STAGE_BYTES) >> 4);
+        const int ksteps = (rows + 15) >> 4;
+        auto pv_step = [&](int ks) {
+          // A = P[:, 16 ks .. 16 ks + 15]: 8 packed TMEM columns inside the 32-column quarter the kv columns belong to
+          const uint32_t a_tmem = tmem_base + kTmemS + h * kHalfKV + (ks >> 1) * 32 + (ks & 1) * 8;
+          const uint32_t acc = (G.first_of_item && h == 0 && ks == 0) ? 0u : 1u;
+          umma_f16_ts(tmem_base + kTmemO, a_tmem, v_desc + (uint64_t)((ks * 16 * C::SUB_BYTES) >> 4), idesc_pv, acc);
+          umma_f16_ts(tmem_base + kTmemL, a_tmem, ones_desc, idesc_l, acc);   // l += P . 1
+        };
+        // full halves (the common case) with compile-time operand offsets: the rolled loop spends ~25 dependent
+        // uniform-datapath instructions per step, about as long as the tensor core needs for the step itself
+        if (ksteps == kHalfKV / 16) {
+#pragma unroll
+          for (int ks = 0; ks < kHalfKV / 16; ++ks) pv_step(ks);
+        } else {
+#pragma unroll 1
+          for (int ks = 0; ks < ksteps; ++ks) pv_step(ks);
+        }
+        umma_commit(&kv_empty[stage]);
+        advance();
+        if (h) ++pv_cntB; else ++pv_cntA;
+        umma_commit(pv_half);
+        DS_TRACE_EV(26 + h);
+        if (G.last_of_item && (h == 1 || G.rowsB == 0)) {
+          umma_commit(o_full);
+          ++items_pv;
+        }
+      };
+      LiteGroup prev = {};
+      bool have_prev = false;
+      for_each_group_lite(p, [&](const LiteGroup& G) {
+        if (have_prev) issue_pv(prev, 0);
+        issue_qk(G, 0);
+        if (have_prev && prev.rowsB) issue_pv(prev, 1);
+        if (G.rowsB) issue_qk(G, 1);
+        prev = G;
+        have_prev = true;
+      });
+      if (have_prev) {
+        issue_pv(prev, 0);
+        if (prev.rowsB) issue_pv(prev, 1);
+      }
+    }
+  } else if (warp >= kWarpSoftmax0) {
+    // ------------------------------------------------------------------ softmax
+    const int qtr = (warp - kWarpSoftmax0) >> 2;            // which 32 columns of each S half
+    const int quad = warp & 3;                   // TMEM lane quadrant this warp may touch
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    const uint32_t s_col = tmem_base + lane_addr + kTmemS + qtr * 32;
-    const uint32_t p_col = tmem_base + lane_addr + kTmemP + qtr * 16;   // + 64 * (h & 1)
+    const uint32_t s_col = tmem_base + lane_addr + kTmemS + qtr * 32;   // + h * 128; P goes to the first 16 of the 32
     const uint32_t o_col = tmem_base + lane_addr + kTmemO;
     const float sl2 = p.scale_log2;
-    uint32_t hs = 0, items = 0;   // half-steps, items seen
-    float m_run = 0.f, l_run = 0.f;
-    DS_ACCT_DECL
+    uint32_t cntA = 0, cntB = 0, w = 0;   // halves A / B seen, half-steps
+    float m_run = 0.f;
 #ifdef DS_TRACE
     int _tr_n = 0;
     const int _tr_slot = warp == kWarpSoftmax0 ? 2 : 3;
-    const bool _tr_on = p.trace && blockIdx.x == 0 && lane == 0 && (warp == kWarpSoftmax0 || warp == kWarpEpi0 - 1);
+    const bool _tr_on = p.trace && blockIdx.x == 0 && lane == 0 && (warp == kWarpSoftmax0 || warp == 25);
 #endif
 
-    for_each_half(p, [&](const HalfInfo& X) {
-      const int nv = max(0, min(X.rows - qtr * 32, 32));   // valid columns of this thread's 32
-      const bool first = X.first_of_item;
-      DS_TRACE_EV(30);
-      DS_ACCT_END(4);   // everything between the previous arrive and here (loop overhead)
-      DS_ACCT_BEGIN();
-      mbar_wait(s_full, hs & 1);
-      DS_ACCT_END(0);
-      DS_ACCT_BEGIN();
-      DS_TRACE_EV(32);
-      tc_fence_after_sync();
-      uint32_t v[32];
-      tmem_ld_x32(s_col, v);   // also when nv == 0: stale columns, never used
-      tmem_wait_ld();
-      tc_fence_before_sync();
-      mbar_arrive(s_free);     // S may be overwritten by the next QK
-      // ragged tail (rare): columns past the kv length hold stale data, possibly NaN -- overwrite them with -inf once,
-      // so that the common path below carries no per-column selects (-inf is neutral for the maximum and
-      // exp2(-inf * scale - m) = 0; the host guarantees scale > 0)
-      if (nv < 32) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j >= nv) v[j] = 0xff800000u;
-      }
-      // ---- row maximum of this half-step (4 threads per row exchange through shared memory)
-      float m;
-      {
-        float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          a0 = fmaxf(a0, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
-          a1 = fmaxf(a1, fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
-          a2 = fmaxf(a2, fmaxf(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])));
-          a3 = fmaxf(a3, fmaxf(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])));
-        }
-        m = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
-      }
-      m *= sl2;
-      float* mx = sMax + (hs & 1) * 512;
-      mx[qtr * 128 + row] = m;
-      DS_TRACE_EV(34);
-      DS_ACCT_END(1);   // S load + maximum
-      DS_ACCT_BEGIN();
-      named_bar_sync(1 + quad, 128);   // the four warps of this TMEM quadrant (= of this scheduler) hold the row
-      DS_ACCT_END(2);
-      DS_TRACE_EV(36);
-      const float Mh = fmaxf(fmaxf(mx[row], mx[128 + row]), fmaxf(mx[256 + row], mx[384 + row]));
-      // Lazy running maximum: the first half-step of the item fixes the row's reference m_run; a later one keeps it and
-      // simply lets p = exp2(s - m_run) grow -- up to 2^14 for fp16 P, 2^30 for bf16 -- which 16-bit P and the fp32
-      // accumulators hold without loss (the offset cancels in O / l).  Only beyond that does the reference move, which
-      // rescales O and l (rare; the four threads of the row decide identically).
-      constexpr float kTau = kBf16 ? 30.0f : 14.0f;
-      float alpha = 1.0f;
-      if (first) {
-        m_run = Mh;
-        l_run = 0.f;
-      } else if (Mh > m_run + kTau) {
-        alpha = fast_exp2(m_run - Mh);
-        m_run = Mh;
-        l_run *= alpha;
-      }
-      if (qtr == 0 && !first) {
-        // the first-quarter thread of a row rescales O before P is released
-        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
-          mbar_wait(&p_free[(hs - 1) & 1], ((hs - 1) >> 1) & 1);   // PV(hs - 1) has landed in O
-          tc_fence_after_sync();
+    for_each_group_lite(p, [&](const LiteGroup& G) {
+      const int n_half = G.rowsB ? 2 : 1;
 #pragma unroll 1
-          for (int c = 0; c < C::D_PAD / 16; ++c) {
-            uint32_t o[16];
-            tmem_ld_x16(o_col + c * 16, o);
-            tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
-            tmem_st_x16(o_col + c * 16, o);
-          }
-        }
-      }
-      // P buffer hs & 1 was last read by PV(hs - 2)
-      DS_ACCT_BEGIN();
-      if (hs >= 2) {
-        mbar_wait(&p_free[hs & 1], ((hs >> 1) - 1) & 1);
+      for (int h = 0; h < n_half; ++h, ++w) {
+        const int nv = max(0, min((h ? G.rowsB : G.rowsA) - qtr * 32, 32));   // valid columns of this thread's 32
+        const bool first = G.first_of_item && h == 0;
+        DS_TRACE_EV(30 + h);
+        mbar_wait(&s_full[h], (h ? cntB : cntA) & 1);
+        DS_TRACE_EV(32 + h);
         tc_fence_after_sync();
-      }
-      DS_ACCT_END(5);
-      DS_ACCT_BEGIN();
-      // ---- p = exp2(s * scale - m) as packed 16-bit pairs (the A operand of the PV product); row sum in fp32
-      if (nv > 0) {
-        uint32_t pk[16];
-        const uint64_t sl2_2 = f2_pack(sl2, sl2), nm_2 = f2_pack(-m_run, -m_run);
-        uint64_t ls = 0ull;
+        uint32_t v[32];
+        tmem_ld_x32(s_col + h * kHalfKV, v);   // also when nv == 0: stale columns, never used
+        tmem_wait_ld();
+        // ragged tail (rare): columns past the kv length hold stale data, possibly NaN -- overwrite them with -inf once,
+        // so that the common path below carries no per-column selects (-inf is neutral for the maximum and
+        // exp2(-inf * scale - m) = 0; the host guarantees scale > 0)
+        if (nv < 32) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float x0, x1, e0, e1;
-          f2_unpack(f2_fma(f2_pack_u(v[j], v[j + 1]), sl2_2, nm_2), x0, x1);
-          // the MUFU pipe (16 ex2 / clk / SM) is what bounds this phase: every kPolyStride-th pair is evaluated on the
-          // FMA pipe instead
-          constexpr int kPolyStride = C::POLY_STRIDE;
-          if (kPolyStride > 0 && ((j >> 1) % (kPolyStride > 0 ? kPolyStride : 1)) == 0) {
-            exp2_poly_f2(x0, x1, e0, e1);
-          } else {
-            e0 = fast_exp2(x0);
-            e1 = fast_exp2(x1);
-          }
-          ls = f2_add(ls, f2_pack(e0, e1));
-          pk[j >> 1] = pack2<kBf16>(e0, e1);
+          for (int j = 0; j < 32; ++j)
+            if (j >= nv) v[j] = 0xff800000u;
         }
-        l_run += f2_hsum(ls);
-        tmem_st_x16(p_col + (hs & 1) * 64, pk);
+        // ---- row maximum of this half (4 threads per row exchange through shared memory)
+        float m;
+        {
+          float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            a0 = fmaxf(a0, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+            a1 = fmaxf(a1, fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+            a2 = fmaxf(a2, fmaxf(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])));
+            a3 = fmaxf(a3, fmaxf(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])));
+          }
+          m = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+        }
+        m *= sl2;
+        float* mx = sMax + (w & 1) * 512;
+        mx[qtr * 128 + row] = m;
+        DS_TRACE_EV(34 + h);
+        named_bar_sync(1 + quad, 128);   // the four warps of this TMEM quadrant (= of this scheduler) hold the row
+        DS_TRACE_EV(36 + h);
+        const float Mh = fmaxf(fmaxf(mx[row], mx[128 + row]), fmaxf(mx[256 + row], mx[384 + row]));
+        // Lazy running maximum: the first half of the item fixes the row's reference m_run; a later half keeps it and
+        // simply lets p = exp2(s - m_run) grow -- up to 2^14 for fp16 P, 2^30 for bf16 -- which 16-bit P and the fp32
+        // accumulators hold without loss (the offset cancels in O / l).  Only beyond that does the reference move, which
+        // rescales O and l (rare; the four threads of the row decide identically).
+        constexpr float kTau = kBf16 ? 30.0f : 14.0f;
+        float alpha = 1.0f;
+        if (first) {
+          m_run = Mh;
+        } else if (Mh > m_run + kTau) {
+          alpha = fast_exp2(m_run - Mh);
+          m_run = Mh;
+        }
+        if (qtr == 0 && !first) {
+          // the first-quarter thread of a row rescales O and l before P is released
+          if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+            mbar_wait(pv_half, (w - 1) & 1);   // the previous half's PV has landed in O (phases <= w-2 are known complete)
+            tc_fence_after_sync();
+#pragma unroll 1
+            for (int c = 0; c < C::D_PAD / 16; ++c) {
+              uint32_t o[16];
+              tmem_ld_x16(o_col + c * 16, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+              tmem_st_x16(o_col + c * 16, o);
+            }
+            const uint32_t l_addr = tmem_base + lane_addr + kTmemL;
+            const float lv = __uint_as_float(tmem_ld_x1(l_addr));
+            tmem_wait_ld();
+            tmem_st_x1(l_addr, __float_as_uint(lv * alpha));
+          }
+        }
+        // ---- p = exp2(s * scale - m), written as packed 16-bit pairs over the first half of the columns just read (the A
+        //      operand of the PV product); the row sum is taken by the tensor core (ones column)
+        if (nv > 0) {
+          uint32_t pk[16];
+          const uint64_t sl2_2 = f2_pack(sl2, sl2), nm_2 = f2_pack(-m_run, -m_run);
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float x0, x1, e0, e1;
+            f2_unpack(f2_fma(f2_pack_u(v[j], v[j + 1]), sl2_2, nm_2), x0, x1);
+            // the MUFU pipe (16 ex2 / clk / SM) is what bounds this phase: every kPolyStride-th pair is evaluated on the
+            // FMA pipe instead
+            constexpr int kPolyStride = C::POLY_STRIDE;
+            if (kPolyStride > 0 && ((j >> 1) % (kPolyStride > 0 ? kPolyStride : 1)) == 0) {
+              exp2_poly_f2(x0, x1, e0, e1);
+            } else {
+              e0 = fast_exp2(x0);
+              e1 = fast_exp2(x1);
+            }
+            pk[j >> 1] = pack2<kBf16>(e0, e1);
+          }
+          tmem_st_x16(s_col + h * kHalfKV, pk);
+        }
+        tmem_wait_st();
+        tc_fence_before_sync();
+        mbar_arrive(&p_full[h]);
+        DS_TRACE_EV(38 + h);
+        if (h) ++cntB; else ++cntA;
       }
-      if (X.last_of_item) {
-        sL[(items & 3) * 512 + qtr * 128 + row] = l_run;   // read by the epilogue after o_full of this item
-        ++items;
-      }
-      tmem_wait_st();
-      tc_fence_before_sync();
-      mbar_arrive(&p_full[hs & 1]);
-      DS_ACCT_END(3);   // exponentials + P store
-      DS_ACCT_BEGIN();
-      DS_TRACE_EV(38);
-      ++hs;
     });
-    if (lane == 0 && warp == kWarpSoftmax0) DS_ACCT_FLUSH(2);
-    if (lane == 0 && warp == kWarpEpi0 - 1) DS_ACCT_FLUSH(3);
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 16-23)
-    reg_alloc<kRegsEpi>();
+    // ------------------------------------------------------------------ epilogue (warps 2-9)
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    const int dh = (warp - kWarpEpi0) >> 2;               // which half of the 16-column chunks of O
+    const int dh = (warp - 2) >> 2;                       // which half of the 16-column chunks of O
     constexpr int NC_ALL = C::D_PAD / 16;
     constexpr int NC0 = (NC_ALL + 1) / 2;                 // chunks of the first half (the second gets the rest)
     const int c_base = dh ? NC0 : 0;
     const uint32_t o_col = tmem_base + lane_addr + kTmemO + c_base * 16;
     const uint32_t os_col = tmem_base + lane_addr + kTmemOs + c_base * 8;
     const int tiles = p.B * p.H * p.n_qt;
-    const int nc_mine = dh ? NC_ALL - NC0 : NC0;
     uint32_t n = 0;   // items seen
 #ifdef DS_TRACE
     int _tr_n = 0;
     const int _tr_slot = 4;
-    const bool _tr_on = p.trace && blockIdx.x == 0 && lane == 0 && warp == kWarpEpi0;
+    const bool _tr_on = p.trace && blockIdx.x == 0 && lane == 0 && warp == 2;
 #endif
     float ns_tile = 0.f;  // |O_self|^2 of the current stream (meaningful on the reducing thread)
-    DS_ACCT_DECL
-    for_each_half(p, [&](const HalfInfo& X) {
-      if (!X.last_of_item) return;
+    for_each_group(p, [&](const GroupInfo& G) {
+      if (!G.last_of_item) return;
       const uint32_t par = n & 1;
       // one phase per item; the tensor core cannot complete the next item before this warp has released O
-      DS_ACCT_BEGIN();
       mbar_wait(o_full, par);
-      DS_ACCT_END(0);
-      DS_ACCT_BEGIN();
       DS_TRACE_EV(40);
+
+      const bool row_ok = G.qt * kBlockQ + row < p.Sq;
       tc_fence_after_sync();
-      // this thread's part of O -> registers, all chunks in flight at once; then O goes straight back to the tensor core
-      uint32_t o[NC0][16];
-#pragma unroll
-      for (int c = 0; c < NC0; ++c)
-        if (c < nc_mine) tmem_ld_x16(o_col + c * 16, o[c]);
       float inv_l;
       {
-        const float* sl = sL + (n & 3) * 512 + row;
-        inv_l = 1.0f / ((sl[0] + sl[128]) + (sl[256] + sl[384]));
+        const uint32_t lv = tmem_ld_x1(tmem_base + lane_addr + kTmemL);
+        tmem_wait_ld();
+        inv_l = 1.0f / __uint_as_float(lv);
       }
-      tmem_wait_ld();
-      tc_fence_before_sync();
-      mbar_arrive(o_empty);
-      DS_ACCT_END(1);   // O -> registers
-      DS_ACCT_BEGIN();
-      DS_TRACE_EV(42);
-
-      const bool row_ok = X.qt * kBlockQ + row < p.Sq;
       // cosine: (acc0+acc1) = dot (cross) or |Os|^2 (self), (acc2+acc3) = |Oc|^2; mse: (acc0+acc1) = sum of squared differences
       uint64_t acc01 = 0ull, acc23 = 0ull;   // packed fp32 pairs, (+0.f, +0.f)
       uint8_t* out_row = nullptr;
       if constexpr (MODE == ATTN_MODE_STORE)
-        out_row = static_cast<uint8_t*>(p.out) + 2 * ((int64_t)X.b * p.out_sb + (int64_t)X.h * p.out_sh +
-                                                     (int64_t)(X.qt * kBlockQ + row) * p.out_ss + c_base * 16);
-      const bool cross = (MODE != ATTN_MODE_STORE) && !X.self;
-      uint32_t os[2][8];
+        out_row = static_cast<uint8_t*>(p.out) + 2 * ((int64_t)G.b * p.out_sb + (int64_t)G.h * p.out_sh +
+                                                     (int64_t)(G.qt * kBlockQ + row) * p.out_ss + c_base * 16);
+      const bool cross = (MODE != ATTN_MODE_STORE) && !G.self;
+      constexpr int NC = NC0;                 // trip count of the unrolled loop; the second half may own one chunk less
+      const int nc_mine = dh ? NC_ALL - NC0 : NC0;
+      // software pipeline over the 16-column chunks of O: the TMEM loads of chunk c+1 are in flight while chunk c is
+      // consumed; O is released to the tensor core as soon as its last chunk has landed in registers
+      uint32_t v[2][16], os[2][8];
+      tmem_ld_x16(o_col, v[0]);
       if (cross) tmem_ld_x8(os_col, os[0]);
+      tmem_wait_ld();
 #pragma unroll
-      for (int c = 0; c < NC0; ++c) {
+      for (int c = 0; c < NC; ++c) {
         const int cur = c & 1;
         if (c >= nc_mine) break;
-        if (cross) {
-          tmem_wait_ld();
-          if (c + 1 < nc_mine) tmem_ld_x8(os_col + (c + 1) * 8, os[cur ^ 1]);
+        if (c + 1 < nc_mine) {
+          tmem_ld_x16(o_col + (c + 1) * 16, v[cur ^ 1]);
+          if (cross) tmem_ld_x8(os_col + (c + 1) * 8, os[cur ^ 1]);
+        } else {
+          tc_fence_before_sync();
+          mbar_arrive(o_empty);
         }
         if constexpr (MODE == ATTN_MODE_STORE) {
           uint32_t pk[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            pk[j] = pack2<kBf16>(__uint_as_float(o[c][2 * j]) * inv_l, __uint_as_float(o[c][2 * j + 1]) * inv_l);
+            pk[j] = pack2<kBf16>(__uint_as_float(v[cur][2 * j]) * inv_l, __uint_as_float(v[cur][2 * j + 1]) * inv_l);
           if (row_ok) {
 #pragma unroll
             for (int hlf = 0; hlf < 2; ++hlf) {
@@ -660,14 +642,14 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           uint32_t pk[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            pk[j] = pack2<kBf16>(__uint_as_float(o[c][2 * j]) * inv_l, __uint_as_float(o[c][2 * j + 1]) * inv_l);
+            pk[j] = pack2<kBf16>(__uint_as_float(v[cur][2 * j]) * inv_l, __uint_as_float(v[cur][2 * j + 1]) * inv_l);
           tmem_st_x8(os_col + c * 8, pk);
           if constexpr (MODE == ATTN_MODE_COS) {
             // |O_self|^2 from the unrounded values, normalised once per row below (differs from the norm of the
             // rounded vector by O(eps^2))
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
-              const uint64_t o2 = f2_pack_u(o[c][j], o[c][j + 1]);
+              const uint64_t o2 = f2_pack_u(v[cur][j], v[cur][j + 1]);
               acc01 = f2_fma(o2, o2, acc01);
             }
           }
@@ -676,7 +658,7 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float2 sv = unpack2<kBf16>(os[cur][j]);
-            const uint64_t o2 = f2_pack_u(o[c][2 * j], o[c][2 * j + 1]);
+            const uint64_t o2 = f2_pack_u(v[cur][2 * j], v[cur][2 * j + 1]);
             acc01 = f2_fma(o2, f2_pack(sv.x, sv.y), acc01);
             acc23 = f2_fma(o2, o2, acc23);
           }
@@ -688,17 +670,18 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           for (int j = 0; j < 8; ++j) {
             const float2 sv = unpack2<kBf16>(os[cur][j]);
             float x0, x1;
-            f2_unpack(f2_mul(f2_pack_u(o[c][2 * j], o[c][2 * j + 1]), inv_l2), x0, x1);
+            f2_unpack(f2_mul(f2_pack_u(v[cur][2 * j], v[cur][2 * j + 1]), inv_l2), x0, x1);
             const float2 ov = unpack2<kBf16>(pack2<kBf16>(x0, x1));
             const uint64_t d2 = f2_add(f2_pack(ov.x, ov.y), f2_pack(-sv.x, -sv.y));
             acc01 = f2_fma(d2, d2, acc01);
           }
         }
+        if (c + 1 < nc_mine) tmem_wait_ld();
       }
       if constexpr (MODE != ATTN_MODE_STORE) {
-        if (X.self) tmem_wait_st();
+        if (G.self) tmem_wait_st();
         float r0, r1;   // cross: (dot, |Oc|^2) or (sq, 0); self: (|Os|^2, 0)
-        if (X.self) {
+        if (G.self) {
           r0 = f2_hsum(acc01) * inv_l * inv_l;
           r1 = 0.f;
         } else if constexpr (MODE == ATTN_MODE_COS) {
@@ -709,7 +692,7 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           r1 = 0.f;
         }
         if (!row_ok) r0 = r1 = 0.f;
-        // fixed-order reduction over the 128 rows: shuffle tree, then the eight warps in order
+        // fixed-order reduction over the 128 rows: shuffle tree, then warps 0..3 in order
         r0 = warp_sum(r0);
         r1 = warp_sum(r1);
         float* red = sRed + par * 16;   // [8 warps][2]
@@ -718,23 +701,21 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           red[(dh * 4 + quad) * 2 + 1] = r1;
         }
         named_bar_sync(5, 256);
-        if (warp == kWarpEpi0 && lane == 0) {
+        if (warp == 2 && lane == 0) {
           const float t0 = ((red[0] + red[2]) + (red[4] + red[6])) + ((red[8] + red[10]) + (red[12] + red[14]));
           const float t1 = ((red[1] + red[3]) + (red[5] + red[7])) + ((red[9] + red[11]) + (red[13] + red[15]));
-          if (X.self) {
+          if (G.self) {
             ns_tile = t0;
           } else if constexpr (MODE == ATTN_MODE_COS) {
-            p.part[(size_t)X.entry * tiles + X.bh * p.n_qt + X.qt] = make_float4(t0, t1, ns_tile, 0.f);
+            p.part[(size_t)G.entry * tiles + G.bh * p.n_qt + G.qt] = make_float4(t0, t1, ns_tile, 0.f);
           } else {
-            p.part[(size_t)X.entry * tiles + X.bh * p.n_qt + X.qt] = make_float4(0.f, 0.f, 0.f, t0);
+            p.part[(size_t)G.entry * tiles + G.bh * p.n_qt + G.qt] = make_float4(0.f, 0.f, 0.f, t0);
           }
         }
       }
-      DS_ACCT_END(2);   // arithmetic + reduction
       DS_TRACE_EV(41);
       ++n;
     });
-    if (lane == 0 && warp == kWarpEpi0) DS_ACCT_FLUSH(4);
   }
   tc_fence_before_sync();
   __syncthreads();

@@ -83,6 +83,35 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+// non-blocking probe of a phase
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// try_wait without a suspend-time hint
+__device__ __forceinline__ bool mbar_try_wait_nohint(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
 #ifndef DS_WATCHDOG_NS
 #define DS_WATCHDOG_NS 4000000000ull  // 4 s: a stuck pipeline traps instead of hanging the GPU
 #endif
@@ -92,6 +121,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // role, and these kernels live or die by their instruction-cache footprint.  A stuck pipeline traps after 2^10 failed
 // try_waits (each may suspend for the hint time: seconds in total); build with -DDS_WATCHDOG_VERBOSE to have it say where.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef DS_FASTWAIT
+  // A try_wait WITHOUT the suspend hint returns ~30 clocks after issue when the phase has already completed (the hinted
+  // form costs ~100-130 even then, profiles/r2p_wait_costs.txt) -- but under the board power cap the extra probe cost 4% of
+  // the sustained rate of the attention kernel (profiles/r2s_power_bisect.txt): off.
+  if (mbar_try_wait_nohint(bar, parity)) return;
+#endif
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins == (1u << 10)) {
@@ -149,6 +184,13 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
       "r"(c3), "r"(c4)
       : "memory");
+}
+
+// TMA prefetch of a 5-D box into L2 (no shared-memory destination, no completion signal)
+__device__ __forceinline__ void tma_prefetch_l2_5d(const CUtensorMap* m, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
 }
 
 // TMA store of a 2-D box from shared memory (bulk async group of the issuing thread)
