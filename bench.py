@@ -14,7 +14,14 @@ so every step streams its inputs from HBM).  metric = scored pairs / second, who
 The JSON line also carries
   roofline      the fused attention kernel: executed flops (7 directional attentions per triplet x
                 4*B*H*S*S*D) / device time of that kernel (CUDA events recorded by the library around the launch,
-                on the launching stream) vs the measured bf16 tensor peak of MEASURED_PEAKS.json
+                on the launching stream) vs the measured BURST bf16 tensor peak of MEASURED_PEAKS.json (frac), with the
+                fraction of the sustained peak beside it (frac_sustained)
+  torch_cuda_reference   the reference's own lines (4 x F.scaled_dot_product_attention + 2 x F.cosine_similarity,
+                diffsim/diffsim.py:177-197) on the SAME GPU: per pair as the reference executes them, batched, and
+                with flash_attn 2.8 -- the GPU number the kernels have to beat
+  roofline_cfg4 / roofline_cfg5   K1 on the SDXL / DiT-XL/2 shapes of BASELINE.json configs[3], [4]
+  retrieval     BASELINE.json configs[2]: the Sref-shaped 2032 x 2032 all-pairs AAS matrix, row-block sharded over the
+                ranks (strong scaling; the one path with a collective: NCCL all-gather of K / V)
   cpu_baseline  the reference's own torch lines (4 SDPA + 2 cosine per pair, diffsim/diffsim.py:177-197) on the
                 host cores, bounded sample
   e2e           the same metric through the hook-input boundary (HostHiddenTripletScorer): pinned host hidden states
@@ -36,7 +43,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SHAPE = (2, 8, 256, 160)  # SD-1.5 512^2 up_blocks layer 0
-DRAM_BYTES_PER_TRIPLET = (8.687563e9 + 8.980992e6) / 512  # ncu --set full, profiles/r1final_attn_ncu_summary.txt
+# dram__bytes_read.sum + dram__bytes_write.sum of K1 per triplet, from the ncu --set full capture named in TRAFFIC_SOURCE
+DRAM_BYTES_PER_TRIPLET = (8.687563e9 + 8.980992e6) / 512
+TRAFFIC_SOURCE = ("profiles/r1final_attn_ncu_summary.txt (ncu --set full of this bench at 512 triplets per launch, commit ccddf32; "
+                  "the round-2 kernel differs only in its work-list walker: same loads)")
 WORKLOAD = "nights_2afc_triplets_sd15_512_up0_cosine"
 METRIC = "scored_pairs_per_sec"
 
@@ -205,6 +215,232 @@ def run_reference_arm(args):
     return 0
 
 
+
+# ------------------------------------------------------------------------------------------------------
+# legs of the GPU arm that are not the headline
+# ------------------------------------------------------------------------------------------------------
+def _timed_ms(fn, iters, dev):
+    import torch
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1) / iters
+
+
+def shape_roofline(name, shape, n_pairs, dtype, dev, peaks, packed_qkv=False, iters=5):
+    """K1 on another BASELINE shape: n_pairs AAS pairs (4 attentions each; the kernel runs 2 self + 2 cross per pair) through
+    ds_aas_pairs; kernel time from the library's own CUDA events.  packed_qkv: q, k, v are views of one (N,B,S,3,H,D) buffer
+    (DiT's qkv(x) layout, diffsim/diffsim_dit.py:22-23)."""
+    import torch
+    from diffsim_b200 import ops, synth
+
+    B, H, S, D = shape
+    n_img = 2 * n_pairs
+    q, k, v = synth.device_cache(B, H, S, D, n_img, dtype, dev, seed=77)
+    if packed_qkv:
+        mem = torch.empty(n_img, B, S, 3, H, D, dtype=dtype, device=dev)
+        for j, t in enumerate((q, k, v)):
+            mem[:, :, :, j] = t.permute(0, 1, 3, 2, 4)
+        q, k, v = (mem[:, :, :, j].permute(0, 1, 3, 2, 4) for j in range(3))
+    pairs = torch.arange(n_img, dtype=torch.int32, device=dev).view(n_pairs, 2)
+    for _ in range(3):
+        ops.aas_pairs(q, k, v, pairs, "cosine")
+    ops.profile_enable(True)
+    for _ in range(iters):
+        ops.aas_pairs(q, k, v, pairs, "cosine")
+    ms, n = ops.profile_collect()
+    ops.profile_enable(False)
+    ms /= max(1, n)
+    fl = 4.0 * n_pairs * attn_flops(shape)
+    tf = fl / (ms * 1e-3) / 1e12
+    return {"kernel": f"aas_attn_kernel<{D}> {name}", "shape_BHSD": list(shape), "pairs_per_launch": n_pairs, "bound": "tensor",
+            "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"], "traffic": None,
+            "flops_per_launch": fl, "ms_per_launch": ms, "pairs_per_sec": n_pairs / (ms * 1e-3),
+            "layout": "packed qkv (N,B,S,3,H,D)" if packed_qkv else "(N,B,S,H*D) per tensor",
+            "inputs_mib": 3 * n_img * B * H * S * D * 2 / 2**20}
+
+
+def torch_cuda_reference(dtype, dev, n_pairs=64, iters=20):
+    """The reference's own lines on the same GPU: 4 x F.scaled_dot_product_attention + 2 x
+    F.cosine_similarity + (a+b)/2 (diffsim/diffsim.py:177-197) on (B,H,S,D) views in the reference layout --
+    (a) per pair, one call sequence per pair as the reference executes it; (b) the same arithmetic batched over all pairs;
+    (c) flash_attn 2.8 batched, if it runs on this GPU.  CUDA events, >= 20 iterations after warm-up."""
+    import torch
+    import torch.nn.functional as F
+    from diffsim_b200 import synth
+
+    B, H, S, D = SHAPE
+    n_img = 2 * n_pairs
+    q, k, v = synth.device_cache(B, H, S, D, n_img, dtype, dev, seed=55)   # 0.5 GB at 64 pairs: larger than L2
+    fl_pair = 4.0 * attn_flops(SHAPE)
+    out = {"shape_BHSD": list(SHAPE), "dtype": str(dtype).replace("torch.", ""), "pairs": n_pairs, "iters": iters,
+           "torch": torch.__version__, "what": "4 x SDPA + 2 x cosine_similarity per pair, diffsim/diffsim.py:177-197"}
+
+    def pair(a, b):
+        qa, ka, va, qb, kb, vb = q[a], k[a], v[a], q[b], k[b], v[b]
+        a_on_b = F.scaled_dot_product_attention(qa, kb, vb, dropout_p=0.0, is_causal=False)
+        b_on_a = F.scaled_dot_product_attention(qb, ka, va, dropout_p=0.0, is_causal=False)
+        self_a = F.scaled_dot_product_attention(qa, ka, va, dropout_p=0.0, is_causal=False)
+        self_b = F.scaled_dot_product_attention(qb, kb, vb, dropout_p=0.0, is_causal=False)
+        d1 = F.cosine_similarity(a_on_b.reshape(-1).unsqueeze(0), self_a.reshape(-1).unsqueeze(0))
+        d2 = F.cosine_similarity(b_on_a.reshape(-1).unsqueeze(0), self_b.reshape(-1).unsqueeze(0))
+        return (d1 + d2) / 2
+
+    def per_pair():
+        return [pair(2 * i, 2 * i + 1) for i in range(n_pairs)]
+
+    ia = torch.arange(0, n_img, 2, device=dev)
+    ib = ia + 1
+
+    def batched(sdpa):
+        qa, ka, va = (t[ia].flatten(0, 1) for t in (q, k, v))   # (P*B,H,S,D) -- the gather is part of the timed work
+        qb, kb, vb = (t[ib].flatten(0, 1) for t in (q, k, v))
+        a_on_b, b_on_a, self_a, self_b = sdpa(qa, kb, vb), sdpa(qb, ka, va), sdpa(qa, ka, va), sdpa(qb, kb, vb)
+        flat = lambda t: t.reshape(n_pairs, -1)  # noqa: E731
+        return (F.cosine_similarity(flat(a_on_b), flat(self_a)) + F.cosine_similarity(flat(b_on_a), flat(self_b))) / 2
+
+    try:
+        for _ in range(2):
+            per_pair()
+        reps = max(1, iters // 10)
+        ms = _timed_ms(per_pair, reps, dev)
+        out["per_pair"] = {"pairs_per_sec": n_pairs / (ms * 1e-3), "tflops": n_pairs * fl_pair / (ms * 1e-3) / 1e12,
+                           "ms_per_pair": ms / n_pairs, "pair_evaluations_timed": reps * n_pairs}
+        sd = lambda a, b, c: F.scaled_dot_product_attention(a, b, c, dropout_p=0.0, is_causal=False)  # noqa: E731
+        for _ in range(3):
+            ref_scores = batched(sd)
+        ms = _timed_ms(lambda: batched(sd), iters, dev)
+        out["batched"] = {"pairs_per_sec": n_pairs / (ms * 1e-3), "tflops": n_pairs * fl_pair / (ms * 1e-3) / 1e12, "ms": ms}
+        out["scores_checksum"] = float(ref_scores.float().sum())
+    except Exception as e:  # pragma: no cover
+        out["error"] = f"{type(e).__name__}: {e}"[:200]
+    try:
+        from flash_attn import flash_attn_func
+
+        def fa(a, b, c):   # flash_attn wants (batch, seq, heads, dim): a transpose VIEW of the (B,H,S,D) views
+            return flash_attn_func(a.transpose(1, 2), b.transpose(1, 2), c.transpose(1, 2), dropout_p=0.0, causal=False).transpose(1, 2)
+
+        for _ in range(3):
+            fa_scores = batched(fa)
+        ms = _timed_ms(lambda: batched(fa), iters, dev)
+        out["flash_attn"] = {"pairs_per_sec": n_pairs / (ms * 1e-3), "tflops": n_pairs * fl_pair / (ms * 1e-3) / 1e12, "ms": ms,
+                             "max_abs_diff_to_torch_sdpa": float((fa_scores.float() - ref_scores.float()).abs().max())}
+    except Exception as e:
+        out["flash_attn"] = {"unavailable": f"{type(e).__name__}: {e}"[:160]}
+    return out
+
+
+def h2d_ceiling(nbytes, dev, barrier, world, dist):
+    """Plain pinned-host -> device copy of the same byte count the end-to-end leg moves per step, all ranks at once: the
+    ceiling the e2e leg's h2d_gbs is to be read against (max over ranks of the device time)."""
+    import torch
+
+    n = min(int(nbytes), 1 << 30)
+    host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    host.fill_(1)
+    dst = torch.empty(n, dtype=torch.uint8, device=dev)
+    for _ in range(2):
+        dst.copy_(host, non_blocking=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 4
+    e0.record()
+    for _ in range(reps):
+        dst.copy_(host, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {"bytes_per_copy": n, "ms": ms, "gbs_per_gpu": n / (ms * 1e-3) / 1e9, "gbs_all_gpus": world * n / (ms * 1e-3) / 1e9,
+            "what": "one cudaMemcpyAsync of pinned host memory per rank, all ranks concurrently, max over ranks"}
+
+
+def retrieval_leg(args, dtype, dev, rank, world, barrier, dist, peaks):
+    """BASELINE.json configs[2]: Sref-shaped all-pairs retrieval -- N = 2032 synthetic images (508 styles x 4), the directional
+    N x N AAS matrix, images row-block sharded over the ranks, K and V exchanged with one NCCL all_gather each (the only
+    data-path collective of the whole port), row blocks gathered at the end.  STRONG scaling: the work is fixed.  Consumer of
+    the result: the ranked lists retrieval_vis.py:57-68 parses."""
+    import torch
+    from diffsim_b200 import ops, retrieval, scoring, synth
+
+    B, H, S, D = SHAPE
+    N = args.retrieval_images
+    per_style = 4
+    r0, r1 = scoring.row_block(N, rank, world)
+    cache = scoring.QKVCache(*synth.device_style_cache(B, H, S, D, r0, r1, per_style, dtype, dev))
+
+    def step():
+        """ms, max over ranks: [exposed all-gather wait, matrix kernels, gather of the row blocks, total]"""
+        if world > 1:
+            ev = {}
+            dm = scoring.aas_matrix_sharded(cache, "cosine", timings=ev)
+            torch.cuda.synchronize(dev)
+            t = [ev["own_done"].elapsed_time(ev["exchange_done"]),
+                 ev["start"].elapsed_time(ev["own_done"]) + ev["exchange_done"].elapsed_time(ev["block_done"]),
+                 ev["block_done"].elapsed_time(ev["end"]), ev["start"].elapsed_time(ev["end"])]
+        else:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dm = ops.aas_matrix(cache.q, cache.k, cache.v, cache.k, cache.v, "cosine")
+            e1.record()
+            torch.cuda.synchronize(dev)
+            t = [0.0, e0.elapsed_time(e1), 0.0, e0.elapsed_time(e1)]
+        t = torch.tensor(t, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return dm, t.tolist()
+
+    barrier()
+    dm, _ = step()   # warm-up: NCCL communicator, tensor maps, workspaces
+    best = None
+    for _ in range(max(1, args.retrieval_reps)):
+        barrier()
+        dm, t = step()
+        if best is None or t[3] < best[3]:
+            best = t
+    ms_gather, ms_matrix, ms_rows, ms_total = best
+    flops = (N * N + N) * attn_flops(SHAPE)        # N^2 cross attentions (incl. the diagonal) + N self attentions
+    kv_bytes = 2 * N * B * H * S * D * 2
+    recv = (world - 1) / world * kv_bytes if world > 1 else 0
+    res = {"workload": "sref_all_pairs_sd15_512_up0_cosine", "images": N, "shape_BHSD": list(SHAPE), "n_gpus": world,
+           "scaling": "strong", "ms_total": ms_total, "ms_matrix_kernels": ms_matrix, "ms_allgather_kv_exposed": ms_gather,
+           "ms_gather_rows": ms_rows, "scores_per_sec": N * N / (ms_total * 1e-3),
+           "pairs_per_sec": N * (N - 1) / 2 / (ms_total * 1e-3),
+           "attn_tflops_whole_job": flops / (ms_matrix * 1e-3) / 1e12,
+           "attn_tflops_per_gpu": flops / world / (ms_matrix * 1e-3) / 1e12,
+           "frac_of_burst_peak_per_gpu": flops / world / (ms_matrix * 1e-3) / 1e12 / peaks["bf16_tflops"],
+           "allgather_recv_bytes_per_rank": recv,
+           "allgather_gbs_if_fully_exposed": (recv / (ms_gather * 1e-3) / 1e9) if ms_gather > 0.05 else None,
+           "nvlink_peak_gbs_per_dir": 900.0,
+           "exchange": "NCCL all_gather_into_tensor of K and of V, issued asynchronously before the rank scores its rows against its "
+                       "own columns; ms_allgather_kv_exposed is the wait left AFTER that block (the part not hidden)",
+           "timing": "CUDA events on the launching stream, max over ranks, best of %d after one warm-up" % max(1, args.retrieval_reps)}
+    if rank == 0:
+        labels = [i // per_style for i in range(N)]
+        res["retrieval_accuracy"] = retrieval.retrieval_accuracy(scoring.symmetrize(dm), labels, topk=per_style - 1)
+        # bitwise check on a sampled row block: rank 0 rebuilds EVERY image (the generator is deterministic per image) and
+        # recomputes 8 of its rows against all N columns in one unsharded call
+        full = scoring.QKVCache(*synth.device_style_cache(B, H, S, D, 0, N, per_style, dtype, dev))
+        rows = [0, 1, 2, 3, (r1 - r0) // 2, (r1 - r0) // 2 + 1, r1 - r0 - 2, r1 - r0 - 1]
+        idx = torch.tensor(rows, device=dev)
+        mem = [m[idx] for m in full.memory()]
+        sub = scoring.QKVCache(*(m.view(len(rows), B, S, H, D).permute(0, 1, 3, 2, 4) for m in mem))
+        ref = ops.aas_matrix(sub.q, sub.k, sub.v, full.k, full.v, "cosine")
+        res["bitwise_equal_to_rank_local_recompute"] = bool(torch.equal(ref, dm[idx]))
+        res["checked_rows"] = rows
+        del full, ref
+    del cache, dm
+    torch.cuda.empty_cache()
+    return res
+
+
 # ------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------
@@ -221,7 +457,11 @@ def main():
     ap.add_argument("--dtype", default="float16", choices=["float16", "bfloat16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the K2 / K3 secondary roofline measurements")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the K2 / K3 / K4 / cfg4 / cfg5 secondary roofline measurements")
+    ap.add_argument("--no-torch-reference", action="store_true", help="skip the torch-CUDA / flash_attn reference timing")
+    ap.add_argument("--no-retrieval", action="store_true", help="skip the all-pairs retrieval leg (BASELINE configs[2])")
+    ap.add_argument("--retrieval-images", type=int, default=2032)
+    ap.add_argument("--retrieval-reps", type=int, default=1)
     ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: do not bind ranks to their GPU's NUMA-local CPUs")
     ap.add_argument("--profiler-range", action="store_true",
                     help="bracket the timed device-resident steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
@@ -304,20 +544,20 @@ def main():
     peaks = load_peaks()
     kern_ms_per_launch = kern_ms / max(1, kern_n)
     achieved_tflops = attn_per_step * attn_flops(SHAPE) / (kern_ms_per_launch * 1e-3) / 1e12 if kern_n else None
-    # The timed region is a back-to-back train of this one kernel lasting hundreds of ms: the GPU sits at its 1 kW power
-    # cap (see "clocks"), so the denominator is the SUSTAINED measured bf16 figure; the burst figure is reported beside it.
-    sustained = ms_total > 250.0
-    peak = peaks["bf16_tflops_sustained"] if sustained else peaks["bf16_tflops"]
+    # Denominator: the BURST bf16 figure of MEASURED_PEAKS.json (north_star's ">= 60% of bf16 tensor-core peak"); the timed
+    # region is a power-capped train of this one kernel, so the fraction of the SUSTAINED figure is printed beside it.
+    peak = peaks["bf16_tflops"]
     roofline = {
         "kernel": "aas_attn_kernel<160,f16,cos> (fused QK^T -> online softmax -> PV -> cosine partials; tcgen05/TMEM/TMA)",
         "bound": "tensor", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
         "frac": (achieved_tflops / peak) if achieved_tflops else None,
-        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full capture of the same workload at
-        # 512 triplets per launch (profiles/r1t_attn_ncu_summary.txt), scaled to this launch's triplet count
+        "frac_sustained": (achieved_tflops / peaks["bf16_tflops_sustained"]) if achieved_tflops else None,
+        "peak_sustained": peaks["bf16_tflops_sustained"],
+        "peak_source": peaks["source"] + ": burst bf16 figure (frac), sustained bf16 figure (frac_sustained)",
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, per launch: NOT measured in this run -- the per-triplet
+        # figure of the ncu --set full capture named in traffic_source, scaled to this launch's triplet count
         "traffic": DRAM_BYTES_PER_TRIPLET * T, "traffic_algorithmic": 3 * T * cache.bytes_per_image,
-        "peak_source": peaks["source"] + (", sustained bf16 figure (kernel timed inside a long power-capped run)"
-                                          if sustained else ", burst bf16 figure"),
-        "frac_of_burst_peak": (achieved_tflops / peaks["bf16_tflops"]) if achieved_tflops else None,
+        "traffic_source": TRAFFIC_SOURCE,
         "flops_per_launch": attn_per_step * attn_flops(SHAPE), "ms_per_launch": kern_ms_per_launch,
         "launches_timed": kern_n, "share_of_step": (kern_ms_per_launch / ms_per_step) if kern_n else None,
         "algorithmic": "7 directional attentions per triplet x 4*B*H*S*S*D flops (DESIGN.md section 3)",
@@ -361,6 +601,9 @@ def main():
                "api": "diffsim_b200.scoring.HostHiddenTripletScorer.score (pinned host hidden states -> ds_qkv_project -> "
                       "ds_aas_triplets -> counts)",
                "h2d_gbs": hscorer.h2d_bytes / (ms_e * 1e-3) / 1e9, "correct": c_e2e[0]}
+        e2e["h2d_gbs_all_gpus"] = e2e["h2d_gbs"] * world
+        e2e["h2d_ceiling"] = h2d_ceiling(e2e["h2d_bytes_per_step"], dev, barrier, world, dist)
+        e2e["h2d_frac_of_ceiling"] = e2e["h2d_gbs"] / e2e["h2d_ceiling"]["gbs_per_gpu"]
         # K4 alone on the resident copy of the same hidden states (secondary roofline)
         hid_dev = hid_host[: 3 * min(Te, 256)].to(dev)
         outs = [torch.empty(hid_dev.shape[:-1] + (H * D,), dtype=dtype, device=dev) for _ in range(3)]
@@ -449,6 +692,29 @@ def main():
                                         "EXECUTED (36 of 64 256x256 tiles), full_matrix_equivalent the 2*N*N*L of the result",
                                 "diag_minus_one_max": float((outm.diagonal() - 1).abs().max())}
         del feats, outm
+        torch.cuda.empty_cache()
+        # K1 on the shapes of BASELINE.json configs[3] (SDXL 1024^2: the two real up-block layers and the literal "4096 tokens x
+        # 1280 channels") and configs[4] (DiT-XL/2 256^2, packed qkv strides, IPref-shaped pair batch)
+        extra["roofline_cfg4"] = {
+            "sdxl_up0_2x20x1024x64": shape_roofline("SDXL up_blocks[0]", (2, 20, 1024, 64), 64, dtype, dev, peaks),
+            "sdxl_up1_2x10x4096x64": shape_roofline("SDXL up_blocks[1]", (2, 10, 4096, 64), 16, dtype, dev, peaks),
+            "literal_2x20x4096x64": shape_roofline("literal 4096 tokens x 1280 ch", (2, 20, 4096, 64), 8, dtype, dev, peaks)}
+        extra["roofline_cfg5"] = {
+            "dit_xl2_2x16x256x72_packed": shape_roofline("DiT-XL/2 blocks[l].attn", (2, 16, 256, 72), 512, dtype, dev, peaks,
+                                                         packed_qkv=True)}
+        torch.cuda.empty_cache()
+
+    # ---- the reference's own torch lines on this GPU (rank 0) -------------------------------------------------------
+    if rank == 0 and not args.no_torch_reference:
+        torch.cuda.empty_cache()
+        extra["torch_cuda_reference"] = torch_cuda_reference(dtype, dev)
+        torch.cuda.empty_cache()
+
+    # ---- all-pairs retrieval, row-block sharded (every rank; strong scaling; NCCL all-gather of K / V) ----------------
+    if not args.no_retrieval:
+        r = retrieval_leg(args, dtype, dev, rank, world, barrier, dist if world > 1 else None, peaks)
+        if rank == 0:
+            extra["retrieval"] = r
 
     # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------------------------
     cpu = None

@@ -726,7 +726,7 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 
 // dir[t] from the per-tile partials, tiles added in index order (deterministic)
 __global__ void aas_finish_kernel(const float4* __restrict__ part, int64_t n_entries, int tiles, double E, int mode,
-                                  float* __restrict__ dir, int64_t ncols, int64_t ldd) {
+                                  float* __restrict__ dir, int64_t ncols, int64_t ldd, int64_t nrows, int64_t chunk_cols) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= n_entries) return;
   const float4* pp = part + (size_t)t * tiles;
@@ -744,9 +744,18 @@ __global__ void aas_finish_kernel(const float4* __restrict__ part, int64_t n_ent
     double nx = fmax(sqrt((double)nc), 1e-8), ny = fmax(sqrt((double)ns), 1e-8);
     r = (float)((double)d / (nx * ny));
   }
-  // optional matrix layout: entry t = row * ncols + col  ->  dir[row * ldd + col]
-  if (ncols > 0) dir[(t / ncols) * ldd + (t % ncols)] = r;
-  else dir[t] = r;
+  if (ncols > 0) {
+    // matrix layout, entries in column-chunk-major order (matrix_setup_kernel): chunk ch holds, row after row, the
+    // w(ch) = min(chunk_cols, ncols - ch * chunk_cols) columns starting at ch * chunk_cols
+    const int64_t full = nrows * chunk_cols;                 // entries of a full chunk
+    const int64_t ch = t / full;
+    const int64_t w = min(chunk_cols, ncols - ch * chunk_cols);
+    const int64_t rem = t - ch * full;
+    const int64_t row = rem / w, col = ch * chunk_cols + rem % w;
+    dir[row * ldd + col] = r;
+  } else {
+    dir[t] = r;
+  }
 }
 
 __global__ void single_meta_kernel(int32_t* __restrict__ meta) {
@@ -840,16 +849,27 @@ __global__ void triplets_finish_kernel(const float* __restrict__ dir, int64_t n,
   }
 }
 
+// Work list of the N x N matrix.  Groups (and their entries) are laid out COLUMN-CHUNK-MAJOR: group g = ch * n_rows + row
+// scores row image `row` against the columns of chunk ch.  The CTAs of a wave then work on ~74 different rows of the SAME
+// chunk, whose K / V slices of the current (b, h) -- chunk_cols x 2 x S x D x 2 bytes, sized by matrix_plan to a third of
+// the L2 -- stay resident while every row streams over them (row-major order made all CTAs stream all N columns: a 333 MB
+// working set per (b, h) at the Sref shape, kept out of DRAM only by the CTAs happening to run in lock-step).
 __global__ void matrix_setup_kernel(int64_t n_rows, int64_t n_cols, int chunks, int64_t chunk_cols,
                                     int32_t* __restrict__ group_q, int32_t* __restrict__ group_off,
                                     int32_t* __restrict__ kv_idx) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t n_groups = n_rows * chunks;
-  if (i < n_rows * n_cols) kv_idx[i] = (int32_t)(i % n_cols);
+  const int64_t full = n_rows * chunk_cols;
+  if (i < n_rows * n_cols) {
+    const int64_t ch = i / full;
+    const int64_t w = min(chunk_cols, n_cols - ch * chunk_cols);
+    kv_idx[i] = (int32_t)(ch * chunk_cols + (i - ch * full) % w);
+  }
   if (i < n_groups) {
-    int64_t r = i / chunks, ch = i % chunks;
+    const int64_t ch = i / n_rows, r = i % n_rows;
+    const int64_t w = min(chunk_cols, n_cols - ch * chunk_cols);
     group_q[i] = (int32_t)r;
-    group_off[i] = (int32_t)(r * n_cols + min(n_cols, ch * chunk_cols));
+    group_off[i] = (int32_t)(ch * full + r * w);
   }
   if (i == n_groups) group_off[i] = (int32_t)(n_rows * n_cols);
 }
@@ -1103,7 +1123,7 @@ int ds_aas_groups(ds_tensor5 q, ds_tensor5 k_self, ds_tensor5 v_self, ds_tensor5
   rc = launch_attn(a, st);
   if (rc != DS_OK) return rc;
   const double E = (double)a.p.B * a.p.H * a.p.Sq * (double)q.size[4];
-  aas_finish_kernel<<<(unsigned)((n_entries + 127) / 128), 128, 0, st>>>(part, n_entries, tiles, E, mode, dir, 0, 0);
+  aas_finish_kernel<<<(unsigned)((n_entries + 127) / 128), 128, 0, st>>>(part, n_entries, tiles, E, mode, dir, 0, 0, 0, 0);
   DS_CUDA_TRY(cudaGetLastError());
   return DS_OK;
 }
@@ -1194,13 +1214,20 @@ int ds_aas_triplets(ds_tensor5 q, ds_tensor5 k, ds_tensor5 v, const int32_t* tri
   return DS_OK;
 }
 
-static void matrix_plan(const ds_tensor5& q, int64_t n_rows, int64_t n_cols, int* chunks, int64_t* chunk_cols) {
+static void matrix_plan(const ds_tensor5& q, const ds_tensor5& k, int64_t n_rows, int64_t n_cols, int* chunks, int64_t* chunk_cols) {
   const int64_t per_row = q.size[1] * q.size[2] * ((q.size[3] + ds::kBlockQ - 1) / ds::kBlockQ);
-  int64_t c = (4 * 148 + n_rows * per_row - 1) / (n_rows * per_row);  // aim at >= 4 streams per SM
-  int64_t maxc = n_cols / 8;                                          // keep the self recompute <= 1/8 of the work
-  if (c > maxc) c = maxc;
-  if (c < 1) c = 1;
-  int64_t cc = (n_cols + c - 1) / c;
+  // (1) L2 blocking: the K and V slices of one (b, h) of a chunk's columns should fill about a third of the 126 MB L2
+  const int64_t slice_bytes = 2 * k.size[3] * k.size[4] * 2;
+  int64_t cc = (40ll << 20) / (slice_bytes > 0 ? slice_bytes : 1);
+  if (cc > n_cols) cc = n_cols;
+  // (2) enough streams to fill the machine: >= 4 per SM
+  const int64_t want = (4 * 148 + n_rows * per_row - 1) / (n_rows * per_row);
+  if (want > 1) {
+    const int64_t c2 = (n_cols + want - 1) / want;
+    if (c2 < cc) cc = c2;
+  }
+  // (3) the query image's self attention is recomputed once per chunk: keep that <= 1/8 of the work
+  if (cc < 8) cc = n_cols < 8 ? n_cols : 8;
   *chunk_cols = cc;
   *chunks = (int)((n_cols + cc - 1) / cc);
 }
@@ -1210,7 +1237,7 @@ size_t ds_aas_matrix_workspace_bytes(ds_tensor5 q, ds_tensor5 k) {
   if (nr <= 0 || nc <= 0) return 256;
   int chunks;
   int64_t cc;
-  matrix_plan(q, nr, nc, &chunks, &cc);
+  matrix_plan(q, k, nr, nc, &chunks, &cc);
   size_t b = ds_aas_groups_workspace_bytes(q, nr * chunks, nr * nc);
   b += ds::align_up((size_t)(nr * chunks) * 4, 256);
   b += ds::align_up((size_t)(nr * chunks + 1) * 4, 256);
@@ -1228,7 +1255,7 @@ int ds_aas_matrix(ds_tensor5 q, ds_tensor5 k_self, ds_tensor5 v_self, ds_tensor5
   if (nr * nc > INT32_MAX) return fail(DS_ERR_INVALID, "ds_aas_matrix: more than 2^31 entries; split the rows");
   int chunks;
   int64_t cc;
-  matrix_plan(q, nr, nc, &chunks, &cc);
+  matrix_plan(q, k, nr, nc, &chunks, &cc);
   const int64_t G = nr * chunks, T = nr * nc;
   AttnLaunch a;
   a.q = q;
@@ -1263,7 +1290,7 @@ int ds_aas_matrix(ds_tensor5 q, ds_tensor5 k_self, ds_tensor5 v_self, ds_tensor5
   rc = launch_attn(a, st);
   if (rc != DS_OK) return rc;
   const double E = (double)a.p.B * a.p.H * a.p.Sq * (double)q.size[4];
-  aas_finish_kernel<<<(unsigned)((T + 127) / 128), 128, 0, st>>>(part, T, tiles, E, mode, Dm, nc, ldd);
+  aas_finish_kernel<<<(unsigned)((T + 127) / 128), 128, 0, st>>>(part, T, tiles, E, mode, Dm, nc, ldd, nr, cc);
   DS_CUDA_TRY(cudaGetLastError());
   return DS_OK;
 }

@@ -48,7 +48,8 @@ def _need_cuda(*ts: torch.Tensor) -> torch.device:
 
 
 def _workspace(dev: torch.device, nbytes: int, slot: str = "main") -> torch.Tensor:
-    key = (dev.index if dev.index is not None else torch.cuda.current_device(), slot)
+    # one buffer per (device, stream, slot): calls issued on two streams must not share partials
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(dev).cuda_stream, slot)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=dev)

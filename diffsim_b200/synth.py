@@ -211,3 +211,29 @@ def device_hidden(B: int, H: int, S: int, D: int, n_images: int, dtype=torch.flo
         h = alpha * bases[idx] + torch.sqrt(1 - alpha * alpha) * torch.randn(i1 - i0, B, S, C, generator=g, device=device)
         out[i0:i1].copy_(h.to(dtype))
     return out, weight
+
+
+def device_style_cache(B: int, H: int, S: int, D: int, i0: int, i1: int, per_style: int = 4, dtype=torch.float16, device="cuda",
+                       alpha: float = 0.8, seed: int = 2334):
+    """Images [i0, i1) of an Sref-shaped style set (image i belongs to style i // per_style; the images of a style share a
+    base, alpha = 0.8), generated on the device.  Deterministic per image -- the generator is re-seeded per style and per
+    image -- so any rank can build any image of the set (row-block sharded retrieval, and its single-GPU check).
+    Returns q, k, v as (n,B,H,S,D) views over (n,B,S,H*D) memory."""
+    C = H * D
+    g = torch.Generator(device=device).manual_seed(seed)
+    std = 1.0 / math.sqrt(C)
+    Wq = torch.randn(C, C, generator=g, device=device) * (std * 2.2)
+    Wk = torch.randn(C, C, generator=g, device=device) * (std * 2.2)
+    Wv = torch.randn(C, C, generator=g, device=device) * std
+    mems = [torch.empty(i1 - i0, B, S, C, dtype=dtype, device=device) for _ in range(3)]
+    for i in range(i0, i1):
+        gs = torch.Generator(device=device).manual_seed(1000003 + i // per_style)
+        base = torch.randn(1, S, C, generator=gs, device=device).repeat(B, 1, 1)
+        if B > 1:
+            base[1:] += 0.1 * torch.randn(B - 1, S, C, generator=gs, device=device)
+        gi = torch.Generator(device=device).manual_seed(7000001 + i)
+        h = alpha * base + math.sqrt(1 - alpha * alpha) * torch.randn(B, S, C, generator=gi, device=device)
+        mems[0][i - i0] = (h @ Wq).to(dtype)
+        mems[1][i - i0] = (h @ Wk).to(dtype)
+        mems[2][i - i0] = (h @ Wv).to(dtype)
+    return tuple(m.view(i1 - i0, B, S, H, D).permute(0, 1, 3, 2, 4) for m in mems)

@@ -23,28 +23,9 @@ sys.path.insert(0, ROOT)
 
 
 def style_images(B, H, S, D, i0, i1, per_style, dtype, device, alpha=0.8, seed=2334):
-    """Images [i0, i1) of the style set: image i belongs to style i // per_style.  Deterministic per image (the
-    generator is re-seeded per style / image), so any rank can build any image."""
-    import torch
+    from diffsim_b200 import synth
 
-    C = H * D
-    g = torch.Generator(device=device).manual_seed(seed)
-    std = 1.0 / math.sqrt(C)
-    Wq = torch.randn(C, C, generator=g, device=device) * (std * 2.2)
-    Wk = torch.randn(C, C, generator=g, device=device) * (std * 2.2)
-    Wv = torch.randn(C, C, generator=g, device=device) * std
-    mems = [torch.empty(i1 - i0, B, S, C, dtype=dtype, device=device) for _ in range(3)]
-    for i in range(i0, i1):
-        gs = torch.Generator(device=device).manual_seed(1000003 + i // per_style)
-        base = torch.randn(1, S, C, generator=gs, device=device).repeat(B, 1, 1)
-        if B > 1:
-            base[1:] += 0.1 * torch.randn(B - 1, S, C, generator=gs, device=device)
-        gi = torch.Generator(device=device).manual_seed(7000001 + i)
-        h = alpha * base + math.sqrt(1 - alpha * alpha) * torch.randn(B, S, C, generator=gi, device=device)
-        mems[0][i - i0] = (h @ Wq).to(dtype)
-        mems[1][i - i0] = (h @ Wk).to(dtype)
-        mems[2][i - i0] = (h @ Wv).to(dtype)
-    return tuple(m.view(i1 - i0, B, S, H, D).permute(0, 1, 3, 2, 4) for m in mems)
+    return synth.device_style_cache(B, H, S, D, i0, i1, per_style, dtype, device, alpha, seed)
 
 
 def main():
