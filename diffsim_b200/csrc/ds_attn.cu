@@ -724,9 +724,22 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 }
 
 
+// Image indices of a work list against the image counts of the tensors they address.  An out-of-range index would become
+// a TMA coordinate outside the tensor -- TMA zero-fills such loads, so the kernel would return a finite but WRONG score.
+// bad[0] is set instead and aas_finish_kernel turns every score of the call into NaN (loud, no host sync).
+__global__ void validate_groups_kernel(const int32_t* __restrict__ group_q, int64_t n_groups, const int32_t* __restrict__ kv_idx,
+                                       int64_t n_entries, int64_t nq_images, int64_t nk_images, int32_t* __restrict__ bad) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  bool b = false;
+  if (i < n_groups) b |= group_q[i] < 0 || group_q[i] >= nq_images;
+  if (i < n_entries) b |= kv_idx[i] < 0 || kv_idx[i] >= nk_images;
+  if (b) atomicExch(bad, 1);
+}
+
 // dir[t] from the per-tile partials, tiles added in index order (deterministic)
 __global__ void aas_finish_kernel(const float4* __restrict__ part, int64_t n_entries, int tiles, double E, int mode,
-                                  float* __restrict__ dir, int64_t ncols, int64_t ldd, int64_t nrows, int64_t chunk_cols) {
+                                  float* __restrict__ dir, int64_t ncols, int64_t ldd, int64_t nrows, int64_t chunk_cols,
+                                  const int32_t* __restrict__ bad) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= n_entries) return;
   const float4* pp = part + (size_t)t * tiles;
@@ -744,6 +757,7 @@ __global__ void aas_finish_kernel(const float4* __restrict__ part, int64_t n_ent
     double nx = fmax(sqrt((double)nc), 1e-8), ny = fmax(sqrt((double)ns), 1e-8);
     r = (float)((double)d / (nx * ny));
   }
+  if (bad && *bad) r = __int_as_float(0x7fc00000);   // an image index of the work list was out of range
   if (ncols > 0) {
     // matrix layout, entries in column-chunk-major order (matrix_setup_kernel): chunk ch holds, row after row, the
     // w(ch) = min(chunk_cols, ncols - ch * chunk_cols) columns starting at ch * chunk_cols
@@ -1084,7 +1098,7 @@ size_t ds_aas_groups_workspace_bytes(ds_tensor5 q, int64_t n_groups, int64_t n_e
   (void)n_groups;
   if (n_entries <= 0) return 256;
   const int64_t tiles = q.size[1] * q.size[2] * ((q.size[3] + ds::kBlockQ - 1) / ds::kBlockQ);
-  return ds::align_up((size_t)n_entries * tiles * sizeof(float4), 256) + 256;
+  return ds::align_up((size_t)n_entries * tiles * sizeof(float4), 256) + 512;
 }
 
 int ds_aas_groups(ds_tensor5 q, ds_tensor5 k_self, ds_tensor5 v_self, ds_tensor5 k, ds_tensor5 v,
@@ -1107,10 +1121,18 @@ int ds_aas_groups(ds_tensor5 q, ds_tensor5 k_self, ds_tensor5 v_self, ds_tensor5
   const int tiles = a.p.B * a.p.H * a.p.n_qt;
   Workspace w(ws, ws_bytes);
   float4* part = static_cast<float4*>(w.take((size_t)n_entries * tiles * sizeof(float4)));
-  if (!part)
+  int32_t* bad = static_cast<int32_t*>(w.take(sizeof(int32_t)));
+  if (!part || !bad)
     return fail(DS_ERR_WORKSPACE, "ds_aas_groups: workspace too small (%zu given, need %zu)", ws_bytes,
                 ds_aas_groups_workspace_bytes(q, n_groups, n_entries));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DS_CUDA_TRY(cudaMemsetAsync(bad, 0, sizeof(int32_t), st));
+  {
+    const int64_t nv = n_groups > n_entries ? n_groups : n_entries;
+    validate_groups_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>(group_q, n_groups, kv_idx, n_entries, q.size[0],
+                                                                         k.size[0], bad);
+    DS_CUDA_TRY(cudaGetLastError());
+  }
   a.p.group_q = group_q;
   a.p.group_off = group_off;
   a.p.kv_idx = kv_idx;
@@ -1123,7 +1145,7 @@ int ds_aas_groups(ds_tensor5 q, ds_tensor5 k_self, ds_tensor5 v_self, ds_tensor5
   rc = launch_attn(a, st);
   if (rc != DS_OK) return rc;
   const double E = (double)a.p.B * a.p.H * a.p.Sq * (double)q.size[4];
-  aas_finish_kernel<<<(unsigned)((n_entries + 127) / 128), 128, 0, st>>>(part, n_entries, tiles, E, mode, dir, 0, 0, 0, 0);
+  aas_finish_kernel<<<(unsigned)((n_entries + 127) / 128), 128, 0, st>>>(part, n_entries, tiles, E, mode, dir, 0, 0, 0, 0, bad);
   DS_CUDA_TRY(cudaGetLastError());
   return DS_OK;
 }
@@ -1290,7 +1312,7 @@ int ds_aas_matrix(ds_tensor5 q, ds_tensor5 k_self, ds_tensor5 v_self, ds_tensor5
   rc = launch_attn(a, st);
   if (rc != DS_OK) return rc;
   const double E = (double)a.p.B * a.p.H * a.p.Sq * (double)q.size[4];
-  aas_finish_kernel<<<(unsigned)((T + 127) / 128), 128, 0, st>>>(part, T, tiles, E, mode, Dm, nc, ldd, nr, cc);
+  aas_finish_kernel<<<(unsigned)((T + 127) / 128), 128, 0, st>>>(part, T, tiles, E, mode, Dm, nc, ldd, nr, cc, nullptr);
   DS_CUDA_TRY(cudaGetLastError());
   return DS_OK;
 }

@@ -104,15 +104,28 @@ def aas_score_ip_adapter(A, B, similarity: str = "cosine", scale: Optional[float
 # trunks
 # --------------------------------------------------------------------------------------------------------
 class Trunk:
-    """Everything before the hook: image -> (q, k, v) at the target layer."""
+    """Everything before the hook: image -> (q, k, v) at the target layer, in two steps that draw from ONE generator in the
+    reference's order (diffsim/diffsim.py:109-113 then diffsim_pipeline.py:174-176):
+        encode(image)  -> latents      draws the VAE sample
+        forward(latents) -> (q, k, v)  draws the noise
+    so that a scorer can call encode(A), encode(B), forward(A), forward(B) exactly as DiffSim.diffsim does, and
+    extract(image) = forward(encode(image)) serves the cached / batched paths (which, like the reference's own
+    diffsim_value, diffsim/diffsim.py:201-258, seed every image afresh)."""
+
+    def encode(self, image, img_size, generator):
+        raise NotImplementedError
+
+    def forward(self, latents, prompt, target_block, target_layer, target_step, generator) -> QKV:
+        raise NotImplementedError
 
     def extract(self, image, img_size, prompt, target_block, target_layer, target_step, generator) -> QKV:
-        raise NotImplementedError
+        return self.forward(self.encode(image, img_size, generator), prompt, target_block, target_layer, target_step, generator)
 
 
 class SyntheticTrunk(Trunk):
     """Q/K/V at the hook boundary from diffsim_b200.synth: `image` is any hashable id, or 'concept@alpha' to
-    place images of one concept at a chosen similarity."""
+    place images of one concept at a chosen similarity.  NOT a model: it never opens the image.  Scorers take it only when
+    it is passed explicitly (tests, benchmarks, the synthetic CLI)."""
 
     def __init__(self, shape=(2, 8, 256, 160), dtype=torch.float16, device="cuda", layout: str = "sd", seed: int = 2334):
         from .synth import SynthModel
@@ -121,9 +134,11 @@ class SyntheticTrunk(Trunk):
         self.dtype, self.device, self.layout = dtype, device, layout
         self._bases = {}
 
-    def extract(self, image, img_size=512, prompt="", target_block="up_blocks", target_layer=0, target_step=0,
-                generator=None) -> QKV:
-        concept, _, alpha = str(image).partition("@")
+    def encode(self, image, img_size=512, generator=None):
+        return image                                   # the "latents" of the synthetic trunk are the image id itself
+
+    def forward(self, latents, prompt="", target_block="up_blocks", target_layer=0, target_step=0, generator=None) -> QKV:
+        concept, _, alpha = str(latents).partition("@")
         alpha = float(alpha) if alpha else 1.0
         h = int(hashlib.sha1(concept.encode()).hexdigest()[:8], 16)
         if concept not in self._bases:
@@ -132,6 +147,10 @@ class SyntheticTrunk(Trunk):
         q, k, v = self.model.image(self._bases[concept], alpha, self.dtype, self.layout, g)
         mv = lambda t: _to_device_keep_layout(t, self.device)  # noqa: E731
         return mv(q), mv(k), mv(v)
+
+    def extract(self, image, img_size=512, prompt="", target_block="up_blocks", target_layer=0, target_step=0,
+                generator=None) -> QKV:
+        return self.forward(image, prompt, target_block, target_layer, target_step, generator)
 
     def extract_ip(self, image, img_size=512, prompt="", target_block="up_blocks", target_layer=0, target_step=0,
                    generator=None, ip_tokens: int = 16, n_adapters: int = 1):
@@ -154,13 +173,24 @@ def _to_device_keep_layout(t: torch.Tensor, device) -> torch.Tensor:
 
 class DiffusersTrunk(Trunk):
     """SD-1.5 / SDXL trunk on a diffusers pipeline: VAE encode -> add noise at timesteps[target_step] -> ONE UNet
-    forward that stops at the hooked attn1 (diffsim/diffsim.py:92-96,122-155; diffsim_pipeline.py:125-221).
-    Needs `diffusers` and local weights -- neither exists offline, so this class is exercised only where they do."""
+    forward that stops at the hooked attn1 (diffsim/diffsim.py:92-96,122-155; diffsim_pipeline.py:125-221; SDXL:
+    diffsim/diffsim_xl.py:54-63,88-125, diffsim_xl_pipeline.py:195-323).
+    Needs `diffusers` and local weights -- neither exists offline, so this class has only ever met the fake pipelines of
+    tests/test_trunk_cpu.py (INTEGRATION.md says so).
+
+    kind='sd15': prompt embeddings from pipe.encode_prompt(prompt, device, 1, True, None); VAE in the pipeline dtype.
+    kind='sdxl': encode_prompt by keyword (its second positional is prompt_2); the UNet gets
+        added_cond_kwargs = {text_embeds: [neg pooled; pooled], time_ids: [ids; ids]} with
+        ids = pipe._get_add_time_ids((s, s), (0, 0), (s, s), ...) as diffsim_xl_pipeline.py:237-312 builds them; the VAE
+        encodes in float32 and the latents are cast back to the pipeline dtype (diffsim/diffsim_xl.py:58-63)."""
 
     def __init__(self, pipe, device="cuda", dtype=torch.float16, guidance_scale: float = 7.5, kind: str = "sd15",
-                 value_mode: bool = False):
+                 value_mode: bool = False, fused_qkv: bool = True):
+        if kind not in ("sd15", "sdxl"):
+            raise ValueError("kind must be 'sd15' or 'sdxl'")
         self.pipe, self.device, self.dtype, self.guidance_scale, self.kind = pipe, device, dtype, guidance_scale, kind
         self.value_mode = value_mode
+        self.fused_qkv = fused_qkv
         self._prompt_cache = {}
 
     def target_module(self, target_block: str, target_layer):
@@ -183,35 +213,90 @@ class DiffusersTrunk(Trunk):
         return unet.up_blocks[:-1][target_layer[0]].attentions[target_layer[1]].transformer_blocks[target_layer[2]].attn1
 
     @torch.no_grad()
-    def extract(self, image, img_size, prompt, target_block, target_layer, target_step, generator) -> QKV:
-        from . import hooks
+    def encode(self, image, img_size, generator):
         from .imageio import load_image, process_image
 
         pipe = self.pipe
-        x = process_image(load_image(image), img_size).to(self.device, self.dtype)
-        latents = pipe.vae.encode(x).latent_dist.sample(generator=generator) * pipe.vae.config.scaling_factor
-        if prompt not in self._prompt_cache:
+        self._img_size = img_size
+        x = process_image(load_image(image), img_size)
+        if self.kind == "sdxl":
+            pipe.vae.float()                                                        # diffsim/diffsim_xl.py:59-60
+            lat = pipe.vae.encode(x.to(self.device, torch.float32)).latent_dist.sample(generator=generator)
+            return (lat * pipe.vae.config.scaling_factor).to(self.dtype)
+        x = x.to(self.device, self.dtype)
+        return pipe.vae.encode(x).latent_dist.sample(generator=generator) * pipe.vae.config.scaling_factor
+
+    def _conditioning(self, prompt, img_size):
+        """(encoder_hidden_states, extra UNet kwargs), cached per prompt (and image size for SDXL's time ids)."""
+        key = (prompt, img_size if self.kind == "sdxl" else None)
+        if key in self._prompt_cache:
+            return self._prompt_cache[key]
+        pipe = self.pipe
+        if self.kind == "sd15":
             pe, ne = pipe.encode_prompt(prompt, self.device, 1, True, None)[:2]
-            self._prompt_cache[prompt] = torch.cat([ne, pe])
-        embeds = self._prompt_cache[prompt]
+            cond = (torch.cat([ne, pe]), {})
+        else:
+            pe, ne, pooled, neg_pooled = pipe.encode_prompt(prompt=prompt, prompt_2=None, device=self.device,
+                                                            num_images_per_prompt=1, do_classifier_free_guidance=True,
+                                                            negative_prompt=None, negative_prompt_2=None)
+            te2 = getattr(pipe, "text_encoder_2", None)
+            proj_dim = int(pooled.shape[-1]) if te2 is None else te2.config.projection_dim
+            size = (img_size, img_size)
+            ids = pipe._get_add_time_ids(size, (0, 0), size, dtype=pe.dtype, text_encoder_projection_dim=proj_dim)
+            added = {"text_embeds": torch.cat([neg_pooled, pooled], dim=0).to(self.device),
+                     "time_ids": torch.cat([ids, ids], dim=0).to(self.device)}
+            cond = (torch.cat([ne, pe], dim=0).to(self.device), {"added_cond_kwargs": added})
+        self._prompt_cache[key] = cond
+        return cond
+
+    @torch.no_grad()
+    def forward(self, latents, prompt, target_block, target_layer, target_step, generator) -> QKV:
+        from . import hooks
+
+        pipe = self.pipe
+        embeds, extra = self._conditioning(prompt, getattr(self, "_img_size", None))
         pipe.scheduler.set_timesteps(1000, device=self.device)
         t = pipe.scheduler.timesteps[target_step]          # an INDEX into the 1000-step array (diffsim_pipeline.py:153-157)
         noise = torch.randn(latents.shape, generator=generator, device=latents.device, dtype=latents.dtype)
         noisy = pipe.scheduler.add_noise(latents, noise, t.reshape(1))
         module = self.target_module(target_block, target_layer)
-        with hooks.capture(module, hooks.make_sd_pre_hook(early_exit=True)):
+        with hooks.capture(module, hooks.make_sd_pre_hook(early_exit=True, fused_qkv=self.fused_qkv)):
             try:
-                pipe.unet(pipe.scheduler.scale_model_input(torch.cat([noisy] * 2), t), t, encoder_hidden_states=embeds)
+                pipe.unet(pipe.scheduler.scale_model_input(torch.cat([noisy] * 2), t), t, encoder_hidden_states=embeds, **extra)
             except hooks.StopForward:
                 pass
         return tuple(module.stores)
+
+
+def _require_trunk(trunk, who: str):
+    if trunk is None:
+        raise ValueError(
+            f"{who} needs a trunk: pass trunk=DiffusersTrunk(pipe) (a diffusers pipeline with weights) -- or, for tests and "
+            "benchmarks only, trunk=SyntheticTrunk(...), which produces Q/K/V from the image NAME and never reads the image. "
+            "There is no default: a scorer that silently falls back to synthetic tensors returns plausible but meaningless "
+            "scores.")
+    return trunk
+
+
+def _extract_pair(trunk, image_A, image_B, img_size, prompt, target_block, layer, target_step, generator):
+    """Both images through the trunk with ONE generator consumed in the reference's order: VAE sample A, VAE sample B,
+    noise A, noise B (diffsim/diffsim.py:109-113, diffsim_pipeline.py:174-176)."""
+    lat_a = trunk.encode(image_A, img_size, generator)
+    lat_b = trunk.encode(image_B, img_size, generator)
+    A = trunk.forward(lat_a, prompt, target_block, layer, target_step, generator)
+    B = trunk.forward(lat_b, prompt, target_block, layer, target_step, generator)
+    return A, B
+
+
+def _gen_device(trunk, device):
+    return "cpu" if isinstance(trunk, SyntheticTrunk) else device
 
 
 # --------------------------------------------------------------------------------------------------------
 # scorers
 # --------------------------------------------------------------------------------------------------------
 class DiffSim:
-    """SD-1.5 scorer -- diffsim/diffsim.py:80-258."""
+    """SD-1.5 scorer -- diffsim/diffsim.py:80-258.  `trunk` is required (see _require_trunk)."""
 
     def __init__(self, torch_dtype=torch.float16, device="cuda", ip_adapter=False, trunk: Optional[Trunk] = None,
                  match_reference_dtype: bool = True, compat_layer_collapse: bool = True, compat_value_slices: bool = True):
@@ -219,7 +304,7 @@ class DiffSim:
         # the hook that should capture them cannot fire (attn2 receives encoder_hidden_states as a keyword, SURVEY.md
         # section 5); the scoring arithmetic of diffsim/diffsim.py:172-175,184-185 is implemented regardless.
         self.device, self.ip_adapter, self.torch_dtype = device, ip_adapter, torch_dtype
-        self.trunk = trunk if trunk is not None else SyntheticTrunk(dtype=torch_dtype, device=device)
+        self.trunk = _require_trunk(trunk, "DiffSim")
         self.match_reference_dtype = match_reference_dtype
         self.compat_layer_collapse = compat_layer_collapse
         self.compat_value_slices = compat_value_slices
@@ -227,22 +312,23 @@ class DiffSim:
     def diffsim(self, image_A, image_B, img_size, prompt, target_block, target_layer, target_step, ip_adapter=False,
                 seed="2333", device="cuda", similarity="cosine"):
         layer = resolve_sd15_layer(target_layer, self.compat_layer_collapse)
-        generator = get_generator(seed, "cpu" if isinstance(self.trunk, SyntheticTrunk) else device)
+        generator = get_generator(seed, _gen_device(self.trunk, device))
         if ip_adapter:
             if not hasattr(self.trunk, "extract_ip"):
                 raise NotImplementedError("this trunk does not capture IP-Adapter keys / values (extract_ip)")
             A = self.trunk.extract_ip(image_A, img_size, prompt, target_block, layer, target_step, generator)
             B = self.trunk.extract_ip(image_B, img_size, prompt, target_block, layer, target_step, generator)
             return aas_score_ip_adapter(A, B, similarity, None, self.match_reference_dtype)
-        A = self.trunk.extract(image_A, img_size, prompt, target_block, layer, target_step, generator)
-        B = self.trunk.extract(image_B, img_size, prompt, target_block, layer, target_step, generator)
+        A, B = _extract_pair(self.trunk, image_A, image_B, img_size, prompt, target_block, layer, target_step, generator)
         return aas_score(A, B, similarity, None, self.match_reference_dtype)
 
     def extract(self, image, img_size, prompt, target_block, target_layer, target_step, seed="2333", device="cuda"):
-        """(q, k, v) of one image exactly as diffsim() captures them -- same layer indexing -- which is what a cache for
-        batched scoring must hold (drivers.build_cache)."""
+        """(q, k, v) of ONE image at the layer diffsim() scores (same layer indexing) -- what a cache for batched scoring
+        holds (drivers.build_cache).  Seeding is per image (a fresh generator: VAE sample, then noise), as in the
+        reference's diffsim_value; inside diffsim(A, B) the reference draws A's and B's VAE samples before either noise, so
+        image B's tensors there differ from its cached ones for the same seed (RNG contract)."""
         layer = resolve_sd15_layer(target_layer, self.compat_layer_collapse)
-        generator = get_generator(seed, "cpu" if isinstance(self.trunk, SyntheticTrunk) else device)
+        generator = get_generator(seed, _gen_device(self.trunk, device))
         return self.trunk.extract(image, img_size, prompt, target_block, layer, target_step, generator)
 
     def diffsim_value(self, image_A, img_size, prompt, target_block, target_layer, target_step, ip_adapter=False,
@@ -262,47 +348,52 @@ class DiffSim:
 
 
 class diffsim_xl:  # noqa: N801 (the reference's name)
-    """SDXL scorer -- diffsim/diffsim_xl.py:47-155.  target_layer = (block, attention, transformer_block)."""
+    """SDXL scorer -- diffsim/diffsim_xl.py:47-155.  target_layer = (block, attention, transformer_block).
+    `trunk` is required: DiffusersTrunk(pipe, kind='sdxl'), or a SyntheticTrunk for tests."""
 
     def __init__(self, torch_dtype=torch.float16, device="cuda", ip_adapter=False, trunk: Optional[Trunk] = None,
                  match_reference_dtype: bool = True):
         if ip_adapter:
             raise NotImplementedError("the IP-Adapter path is not built")
         self.device = device
-        self.trunk = trunk if trunk is not None else SyntheticTrunk((2, 20, 256, 64), torch_dtype, device)
+        self.trunk = _require_trunk(trunk, "diffsim_xl")
         self.match_reference_dtype = match_reference_dtype
 
     def diffsim_score(self, image_A, image_B, img_size, prompt, target_block, target_layer, target_step, similarity, seed):
-        generator = get_generator(seed, "cpu" if isinstance(self.trunk, SyntheticTrunk) else self.device)
-        A = self.trunk.extract(image_A, img_size, prompt, target_block, target_layer, target_step, generator)
-        B = self.trunk.extract(image_B, img_size, prompt, target_block, target_layer, target_step, generator)
+        generator = get_generator(seed, _gen_device(self.trunk, self.device))
+        A, B = _extract_pair(self.trunk, image_A, image_B, img_size, prompt, target_block, target_layer, target_step, generator)
         return aas_score(A, B, similarity, None, self.match_reference_dtype)
 
     def diffsim_value(self, image_A, img_size, prompt, target_block, target_layer, target_step, seed="2333", device=None):
         """Per-image (q,k,v) -- not in the reference's SDXL scorer; the batched drivers and caches need it."""
-        generator = get_generator(seed, "cpu" if isinstance(self.trunk, SyntheticTrunk) else self.device)
+        generator = get_generator(seed, _gen_device(self.trunk, self.device))
         return self.trunk.extract(image_A, img_size, prompt, target_block, target_layer, target_step, generator)
 
 
 class diffsim_DiT:  # noqa: N801
     """DiT-XL/2 scorer -- diffsim/diffsim_dit.py:29-142.  target_layer[0] = transformer block index (0..27); the hook
-    hands over q, k, v as views into the packed qkv activation, which the kernels read in place."""
+    hands over q, k, v as views into the packed qkv activation, which the kernels read in place.  `trunk` is required (a
+    DiT trunk needs timm + the vendored DiT + a checkpoint: `ckpt` is accepted for signature compatibility and is the
+    trunk's business, not this class's -- it is an error to pass one without a trunk that uses it)."""
 
     def __init__(self, img_size=256, target_step=0, device="cuda", ckpt=None, trunk: Optional[Trunk] = None,
                  match_reference_dtype: bool = True):
         self.device = device
-        self.trunk = trunk if trunk is not None else SyntheticTrunk((2, 16, 256, 72), torch.float16, device, layout="dit")
+        self.trunk = _require_trunk(trunk, "diffsim_DiT")
+        if ckpt is not None and not hasattr(self.trunk, "load_checkpoint"):
+            raise ValueError("ckpt was given but the trunk has no load_checkpoint(): it would be silently ignored")
+        if ckpt is not None:
+            self.trunk.load_checkpoint(ckpt)
         self.match_reference_dtype = match_reference_dtype
 
     def diffsim_score(self, image_A, image_B, img_size, prompt, target_block, target_layer, target_step, similarity, seed):
         layer = target_layer[0] if not isinstance(target_layer, int) else target_layer
-        generator = get_generator(seed, "cpu" if isinstance(self.trunk, SyntheticTrunk) else self.device)
-        A = self.trunk.extract(image_A, img_size, prompt, target_block, layer, target_step, generator)
-        B = self.trunk.extract(image_B, img_size, prompt, target_block, layer, target_step, generator)
+        generator = get_generator(seed, _gen_device(self.trunk, self.device))
+        A, B = _extract_pair(self.trunk, image_A, image_B, img_size, prompt, target_block, layer, target_step, generator)
         return aas_score(A, B, similarity, None, self.match_reference_dtype)
 
     def diffsim_value(self, image_A, img_size, prompt, target_block, target_layer, target_step, seed="2333", device=None):
         """Per-image (q,k,v) -- not in the reference's DiT scorer; the batched drivers and caches need it."""
         layer = target_layer[0] if not isinstance(target_layer, int) else target_layer
-        generator = get_generator(seed, "cpu" if isinstance(self.trunk, SyntheticTrunk) else self.device)
+        generator = get_generator(seed, _gen_device(self.trunk, self.device))
         return self.trunk.extract(image_A, img_size, prompt, target_block, layer, target_step, generator)

@@ -29,17 +29,58 @@ def split_heads(t: torch.Tensor, heads: int) -> torch.Tensor:
     return t.view(B, S, heads, C // heads).transpose(1, 2)
 
 
-def project_qkv(attn, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None):
+def _stacked_qkv_weight(attn):
+    """[W_q; W_k; W_v] (3C, C_in) of a diffusers-style Attention module (+ stacked bias or None), built once per module and
+    rebuilt when a weight is replaced or modified in place (tensor identity and version counter)."""
+    ws = (attn.to_q.weight, attn.to_k.weight, attn.to_v.weight)
+    key = tuple((w.data_ptr(), w._version, w.dtype, w.device) for w in ws)
+    cached = getattr(attn, "_ds_qkv_stack", None)
+    if cached is None or cached[0] != key:
+        weight = torch.cat([w.detach() for w in ws], dim=0).contiguous()
+        bs = (attn.to_q.bias, attn.to_k.bias, attn.to_v.bias)
+        bias = None
+        if any(b is not None for b in bs):
+            bias = torch.cat([b.detach() if b is not None else w.new_zeros(w.shape[0]) for b, w in zip(bs, ws)]).contiguous()
+        cached = (key, weight, bias)
+        attn._ds_qkv_stack = cached
+    return cached[1], cached[2]
+
+
+def _can_fuse(attn, hidden_states) -> bool:
+    """The three projections run as ONE ds_qkv_project call (K4, tcgen05) when the layer is a plain self-attention
+    on a CUDA device in a 16-bit dtype; otherwise the module's own nn.Linear layers are used (CPU trunks of the tests,
+    fp32 trunks, LoRA-wrapped or quantised projections)."""
+    lin = torch.nn.Linear
+    return (hidden_states.is_cuda and hidden_states.dtype in (torch.float16, torch.bfloat16)
+            and all(type(getattr(attn, n, None)) is lin for n in ("to_q", "to_k", "to_v"))
+            and attn.to_q.weight.dtype == hidden_states.dtype
+            and attn.to_q.in_features == attn.to_k.in_features == attn.to_v.in_features
+            and attn.to_q.out_features == attn.to_k.out_features == attn.to_v.out_features
+            and attn.to_q.in_features % 8 == 0 and attn.to_q.out_features % 8 == 0)
+
+
+def project_qkv(attn, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None,
+                already_normed: bool = False, fused_qkv: bool = True, out=None):
     """q, k, v of a diffusers-style Attention module (attributes to_q, to_k, to_v, heads; optional group_norm,
     spatial_norm, norm_cross) -- the projection part of hacked_AttnProcessor2_0.__call__
-    (diffsim/hacked_attn.py:38-77), without the attention and output projection the reference discards."""
-    if getattr(attn, "spatial_norm", None) is not None:
-        raise NotImplementedError("spatial_norm needs temb; use B200AttnProcessor for such layers")
+    (diffsim/hacked_attn.py:38-77), without the attention and output projection the reference discards.
+
+    Self-attention on CUDA: one ds_qkv_project call on the stacked weight [W_q; W_k; W_v] (K4) instead of three
+    nn.Linear; `out` = three pre-allocated (B,S,H*D) tensors (e.g. a slot of a QKVCache) receives the result in place.
+    already_normed: the caller (a processor) has applied attn.spatial_norm(hidden_states, temb) itself -- a pre-hook has no
+    temb and cannot."""
+    if getattr(attn, "spatial_norm", None) is not None and not already_normed:
+        raise NotImplementedError("spatial_norm needs temb, which a forward-pre-hook does not see: set a B200AttnProcessor "
+                                  "on such layers (it applies the norm and passes already_normed=True)")
     if hidden_states.ndim == 4:
         b, c, h, w = hidden_states.shape
         hidden_states = hidden_states.view(b, c, h * w).transpose(1, 2)
     if getattr(attn, "group_norm", None) is not None:
         hidden_states = attn.group_norm(hidden_states.transpose(1, 2)).transpose(1, 2)
+    if encoder_hidden_states is None and fused_qkv and _can_fuse(attn, hidden_states):
+        weight, bias = _stacked_qkv_weight(attn)
+        query, key, value = ops.qkv_project(hidden_states, weight, bias, 3, out=out)
+        return split_heads(query, attn.heads), split_heads(key, attn.heads), split_heads(value, attn.heads)
     query = attn.to_q(hidden_states)
     if encoder_hidden_states is None:
         encoder_hidden_states = hidden_states
@@ -47,15 +88,20 @@ def project_qkv(attn, hidden_states: torch.Tensor, encoder_hidden_states: Option
         encoder_hidden_states = attn.norm_encoder_hidden_states(encoder_hidden_states)
     key = attn.to_k(encoder_hidden_states)
     value = attn.to_v(encoder_hidden_states)
+    if out is not None:
+        for o, t in zip(out, (query, key, value)):
+            o.copy_(t)
+        query, key, value = out
     return split_heads(query, attn.heads), split_heads(key, attn.heads), split_heads(value, attn.heads)
 
 
-def make_sd_pre_hook(early_exit: bool = False):
+def make_sd_pre_hook(early_exit: bool = False, fused_qkv: bool = True, out=None):
     """forward-pre-hook with the contract of sd15_attention_forward_hooked / sdxl_attention_forward_hooked
-    (diffsim/diffsim.py:43-56): `module.stores = [query, key, value]`."""
+    (diffsim/diffsim.py:43-56): `module.stores = [query, key, value]`.  fused_qkv: the projections run as one
+    ds_qkv_project call (K4) where the layer allows it; out: three (B,S,H*D) tensors to capture into (a cache slot)."""
 
     def hook(module, input):
-        q, k, v = project_qkv(module, input[0])
+        q, k, v = project_qkv(module, input[0], fused_qkv=fused_qkv, out=out)
         module.stores = [q, k, v]
         if early_exit:
             raise StopForward()
@@ -63,15 +109,22 @@ def make_sd_pre_hook(early_exit: bool = False):
     return hook
 
 
-def make_dit_pre_hook(early_exit: bool = False):
+def make_dit_pre_hook(early_exit: bool = False, fused_qkv: bool = True):
     """forward-pre-hook for a timm-style Attention block (attributes qkv, num_heads, head_dim, q_norm, k_norm):
     the contract of dit_attention_forward_hook (diffsim/diffsim_dit.py:19-26).  q, k, v are views into the packed
-    qkv activation (strides (N*3*H*D, D, 3*H*D, 1)); the kernels read them in place."""
+    qkv activation (strides (N*3*H*D, D, 3*H*D, 1)); the kernels read them in place.  fused_qkv: module.qkv runs on
+    ds_qkv_project (K4, bias included) when it is a plain 16-bit nn.Linear on CUDA."""
 
     def hook(module, input):
         x = input[0]
         B, N, C = x.shape
-        qkv = module.qkv(x).reshape(B, N, 3, module.num_heads, module.head_dim).permute(2, 0, 3, 1, 4)
+        lin = module.qkv
+        if (fused_qkv and x.is_cuda and x.dtype in (torch.float16, torch.bfloat16) and type(lin) is torch.nn.Linear
+                and lin.weight.dtype == x.dtype and C % 8 == 0 and lin.out_features % 8 == 0):
+            packed = ops.qkv_project(x, lin.weight.detach(), None if lin.bias is None else lin.bias.detach(), 1)[0]
+        else:
+            packed = lin(x)
+        qkv = packed.reshape(B, N, 3, module.num_heads, module.head_dim).permute(2, 0, 3, 1, 4)
         q, k, v = qkv.unbind(0)
         q, k = module.q_norm(q), module.k_norm(k)
         module.stores = [q, k, v]
@@ -95,7 +148,12 @@ def capture(module, hook):
 class B200AttnProcessor:
     """diffusers AttnProcessor protocol (`attn.set_processor(p)`; `p(attn, hidden_states, encoder_hidden_states,
     attention_mask, temb)`) with the hacked return contract of hacked_AttnProcessor2_0 (diffsim/hacked_attn.py:101):
-    (hidden_states, query, key, value, residual).  The scaled-dot-product attention runs in the sm_100a kernel."""
+    (hidden_states, query, key, value, residual).  The scaled-dot-product attention runs in the sm_100a kernel (K1, store
+    mode) and, with fused_qkv (default), the three projections of a self-attention layer in ONE ds_qkv_project call (K4) on
+    the stacked weight -- diffsim/hacked_attn.py:61-77 without a cuBLAS call."""
+
+    def __init__(self, fused_qkv: bool = True):
+        self.fused_qkv = fused_qkv
 
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, *args, **kwargs):
         if attention_mask is not None:
@@ -108,7 +166,8 @@ class B200AttnProcessor:
             batch_size, channel, height, width = hidden_states.shape
             hidden_states = hidden_states.view(batch_size, channel, height * width).transpose(1, 2)
         batch_size = hidden_states.shape[0]
-        query, key, value = project_qkv(attn, hidden_states, encoder_hidden_states)
+        query, key, value = project_qkv(attn, hidden_states, encoder_hidden_states, already_normed=True,
+                                        fused_qkv=self.fused_qkv)
         out = ops.attn_fwd(query, key, value)                       # (B,H,S,D) view over (B,S,H*D)
         head_dim = query.shape[-1]
         hidden_states = out.transpose(1, 2).reshape(batch_size, -1, attn.heads * head_dim).to(query.dtype)
@@ -170,7 +229,7 @@ class B200IPAdapterAttnProcessor(torch.nn.Module):
             batch_size, channel, height, width = hidden_states.shape
             hidden_states = hidden_states.view(batch_size, channel, height * width).transpose(1, 2)
         batch_size = hidden_states.shape[0]
-        query, key, value = project_qkv(attn, hidden_states, encoder_hidden_states)
+        query, key, value = project_qkv(attn, hidden_states, encoder_hidden_states, already_normed=True)
         head_dim = query.shape[-1]
         merge = lambda o: o.transpose(1, 2).reshape(batch_size, -1, attn.heads * head_dim).to(query.dtype)  # noqa: E731
         hidden_states = merge(ops.attn_fwd(query, key, value))

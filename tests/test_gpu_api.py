@@ -37,12 +37,14 @@ def test_diffsim_class_returns_reference_dtype_and_shape():
     s32 = ds32.diffsim("cat@1.0", "cat@0.8", similarity="cosine", **kw)
     assert s32.dtype == torch.float32 and float(s32) == pytest.approx(ref, rel=1e-3)
     # DiT: packed-qkv views are consumed in place
-    dit = diffsim_DiT(256, 600, dev)
+    with pytest.raises(ValueError, match="needs a trunk"):
+        DiffSim(torch.float16, dev)                                   # no silent synthetic default
+    dit = diffsim_DiT(256, 600, dev, trunk=SyntheticTrunk((2, 16, 256, 72), torch.float16, dev, layout="dit"))
     d = dit.diffsim_score("cat@1.0", "cat@0.9", 256, "p", "up_blocks", [14], 600, "cosine", 2334)
     A, Bm = dit.trunk.extract("cat@1.0", target_step=600), dit.trunk.extract("cat@0.9", target_step=600)
     assert A[0].stride()[2] == 3 * 16 * 72
     assert float(d) == pytest.approx(O.aas_pair_score(*[t.cpu() for t in A], *[t.cpu() for t in Bm]), rel=2e-3)
-    xl = diffsim_xl(torch.float16, dev)
+    xl = diffsim_xl(torch.float16, dev, trunk=SyntheticTrunk((2, 20, 256, 64), torch.float16, dev))
     x = xl.diffsim_score("cat@1.0", "cat@0.9", 1024, "p", "up_blocks", [0, 1, 2], 600, "cosine", 2334)
     assert x.shape == (1,) and 0 < float(x) <= 1
 
@@ -81,7 +83,46 @@ def test_hooks_and_processor_follow_the_reference_contract():
         attn(x)
     q, k, v = attn.stores
     assert q.shape == (2, 8, 256, 160) and q.stride() == (327680, 160, 1280, 1)
-    assert torch.equal(q, attn.to_q(x).view(2, 256, 8, 160).transpose(1, 2))
+    # the three projections ran as ONE ds_qkv_project call (K4) on the stacked weight: against the oracle's restatement of
+    # hacked_attn.py:61-77 (float64) and, to an ulp of fp16, against the module's own nn.Linear (cuBLAS)
+    ref_q, ref_k, ref_v = O.reference_capture(x.cpu(), attn.to_q.weight.cpu(), attn.to_k.weight.cpu(), attn.to_v.weight.cpu(), 8)
+    for got, ref in ((q, ref_q), (k, ref_k), (v, ref_v)):
+        assert got.shape == ref.shape
+        assert (got.double().cpu() - ref.double()).abs().max().item() < 4e-3 * max(1.0, ref.abs().max().item())
+    assert (q.float() - attn.to_q(x).view(2, 256, 8, 160).transpose(1, 2).float()).abs().max().item() < 4e-3
+    assert hasattr(attn, "_ds_qkv_stack") and attn._ds_qkv_stack[1].shape == (3 * 1280, 1280)
+    n0 = __import__("diffsim_b200").ops.LAUNCHES
+    with hooks.capture(attn, hooks.make_sd_pre_hook()):
+        attn(x)
+    assert __import__("diffsim_b200").ops.LAUNCHES == n0 + 1      # one library launch per capture, stacked weight cached
+    # fused_qkv=False: the module's own nn.Linear layers, bit for bit
+    with hooks.capture(attn, hooks.make_sd_pre_hook(fused_qkv=False)):
+        attn(x)
+    assert torch.equal(attn.stores[0], attn.to_q(x).view(2, 256, 8, 160).transpose(1, 2))
+    # capture straight into a cache slot
+    from diffsim_b200 import scoring
+
+    cache = scoring.QKVCache.empty(3, 2, 8, 256, 160, torch.float16, dev)
+    slot = [m[1] for m in cache.memory()]
+    with hooks.capture(attn, hooks.make_sd_pre_hook(out=slot)):
+        attn(x)
+    assert attn.stores[0].data_ptr() == cache.q[1].data_ptr() and torch.equal(cache.q[1], q) and torch.equal(cache.v[1], v)
+    # weights replaced in place -> the stacked copy is rebuilt
+    with torch.no_grad():
+        attn.to_k.weight.mul_(0.5)
+    with hooks.capture(attn, hooks.make_sd_pre_hook()):
+        attn(x)
+    assert (attn.stores[1].float() - 0.5 * k.float()).abs().max().item() < 4e-3
+    with torch.no_grad():
+        attn.to_k.weight.mul_(2.0)
+    # a layer with spatial_norm: the pre-hook cannot serve it (no temb) and says so; the processor applies the norm itself
+    attn.spatial_norm = lambda h, temb: h * 2.0
+    with hooks.capture(attn, hooks.make_sd_pre_hook()):
+        with pytest.raises(NotImplementedError, match="spatial_norm"):
+            attn(x)
+    _, q_sn, _, _, _ = hooks.B200AttnProcessor()(attn, x, temb=torch.zeros(1, device=dev))
+    assert (q_sn.float() - 2.0 * q.float()).abs().max().item() < 8e-3
+    attn.spatial_norm = None
     assert len(attn._forward_pre_hooks) == 0                      # removed (the reference accumulates them)
     with hooks.capture(attn, hooks.make_sd_pre_hook(early_exit=True)):
         with pytest.raises(hooks.StopForward):
@@ -109,6 +150,9 @@ def test_hooks_and_processor_follow_the_reference_contract():
         t(xt)
     q, k, v = t.stores
     assert q.shape == (2, 16, 256, 72) and q.stride() == (256 * 3 * 1152, 72, 3 * 1152, 1)
+    # module.qkv (with bias) ran on ds_qkv_project: equal to the module's own Linear up to an ulp of fp16
+    packed = t.qkv(xt).reshape(2, 256, 3, 16, 72).permute(2, 0, 3, 1, 4)
+    assert (q.float() - packed[0].float()).abs().max().item() < 4e-3 and (v.float() - packed[2].float()).abs().max().item() < 4e-3
     from diffsim_b200 import ops
 
     o = ops.attn_fwd(q, k, v)

@@ -91,3 +91,30 @@ def test_full_size_properties_without_an_oracle():
     assert torch.equal(s.reshape(-1), ops.aas_pairs(q[:16], k[:16], v[:16], p16, "cosine"))
     # launching twice gives the same bits (fixed reduction order, no atomics on floats)
     assert torch.equal(dm, ops.aas_matrix(q[:16], k[:16], v[:16], k[:16], v[:16], "cosine"))
+
+
+def test_out_of_range_image_indices_give_nan_not_a_plausible_score():
+    """An index past the cache would become a TMA coordinate outside the tensor (zero-filled: a finite, wrong score): the
+    work list is validated on the device and every score of the call comes back NaN."""
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from diffsim_b200 import ops, synth
+
+    q, k, v = synth.device_cache(2, 4, 128, 64, 6, torch.float16, "cuda", seed=1)
+    good = ops.aas_pairs(q, k, v, [(0, 1), (2, 3)], "cosine")
+    assert torch.isfinite(good).all()
+    for bad_pairs in ([(0, 1), (2, 6)], [(-1, 1)], [(0, 99999)]):
+        assert torch.isnan(ops.aas_pairs(q, k, v, bad_pairs, "cosine")).all()
+    ab, ac, counts, flags = ops.aas_triplets(q, k, v, [(0, 1, 2), (3, 4, 7)], "cosine")
+    assert torch.isnan(ab).all() and torch.isnan(ac).all() and int(counts[0]) == 0
+    assert torch.isfinite(ops.aas_pairs(q, k, v, [(4, 5)], "mse")).all()        # the flag does not stick to the next call
+    # two streams do not share a workspace
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    with torch.cuda.stream(s1):
+        a = ops.aas_pairs(q, k, v, [(0, 1)] * 64, "cosine")
+    with torch.cuda.stream(s2):
+        b = ops.aas_pairs(q, k, v, [(2, 3)] * 64, "cosine")
+    torch.cuda.synchronize()
+    assert torch.equal(a, good[:1].expand(64)) and torch.equal(b, good[1:].expand(64))

@@ -137,3 +137,101 @@ def test_diffsim_value_reproduces_the_reference_slice_quirk_and_extract_does_not
     ds2 = DiffSim(torch.float32, "cpu", trunk=DiffusersTrunk(_Pipe(), "cpu", torch.float32), compat_value_slices=False)
     q2, _, _ = ds2.diffsim_value(*args, seed="2333", device="cpu")
     assert ds2.trunk.pipe.unet.up_blocks[1].attentions[-1].transformer_blocks[-1].attn1.stores[0] is q2
+
+
+class _SDXLPipe(_Pipe):
+    """SDXL-shaped fake: encode_prompt by keyword returning four tensors, _get_add_time_ids, a UNet that insists on
+    added_cond_kwargs, a VAE that records the dtype it is asked to encode in (diffsim/diffsim_xl.py:58-63 upcasts it)."""
+
+    def __init__(self):
+        super().__init__()
+        self.vae_dtypes = []
+        self.vae_float_calls = 0
+        lat = types.SimpleNamespace(sample=lambda generator=None: torch.zeros(1, 4, 8, 8))
+
+        def enc(x):
+            self.vae_dtypes.append(x.dtype)
+            return types.SimpleNamespace(latent_dist=lat)
+
+        def vae_float():
+            self.vae_float_calls += 1
+
+        self.vae = types.SimpleNamespace(encode=enc, float=vae_float, config=types.SimpleNamespace(scaling_factor=0.13025))
+        self.text_encoder_2 = types.SimpleNamespace(config=types.SimpleNamespace(projection_dim=1280))
+        self.unet_kwargs = None
+        unet = self.unet
+
+        def call(sample, t, encoder_hidden_states=None, added_cond_kwargs=None):
+            assert added_cond_kwargs is not None, "the SDXL UNet needs added_cond_kwargs"
+            self.unet_kwargs = added_cond_kwargs
+            return _UNet.__call__(unet, sample, t, encoder_hidden_states)
+
+        self.unet_call = call
+
+    def encode_prompt(self, prompt=None, prompt_2=None, device=None, num_images_per_prompt=1, do_classifier_free_guidance=True,
+                      negative_prompt=None, negative_prompt_2=None):
+        assert isinstance(prompt, str) and prompt_2 is None and not isinstance(device, str) or device == "cpu"
+        self.encode_calls += 1
+        return torch.ones(1, 77, 32), torch.zeros(1, 77, 32), torch.full((1, 1280), 2.0), torch.full((1, 1280), 3.0)
+
+    def _get_add_time_ids(self, original_size, crops, target_size, dtype=None, text_encoder_projection_dim=None):
+        assert text_encoder_projection_dim == 1280
+        return torch.tensor([list(original_size + crops + target_size)], dtype=dtype)
+
+
+def test_sdxl_trunk_passes_added_cond_kwargs_and_encodes_in_fp32():
+    pipe = _SDXLPipe()
+    pipe.unet.__class__ = type("_U", (_UNet,), {"__call__": lambda self, *a, **k: pipe.unet_call(*a, **k)})
+    trunk = DiffusersTrunk(pipe, "cpu", torch.bfloat16, kind="sdxl")
+    img = Image.new("RGB", (20, 12), (200, 30, 90))
+    lat = trunk.encode(img, 32, torch.Generator().manual_seed(1))
+    assert lat.dtype == torch.bfloat16                                                   # latents cast back to the pipeline dtype
+    pipe.vae_dtypes.clear()
+    pipe.vae_float_calls = 0
+    trunk = DiffusersTrunk(pipe, "cpu", torch.float32, kind="sdxl")                      # (the fake UNet computes in fp32)
+    q, k, v = trunk.extract(img, 32, "a photo", "up_blocks", [1, 0, 1], 600, torch.Generator().manual_seed(1))
+    assert pipe.vae_dtypes == [torch.float32] and pipe.vae_float_calls == 1          # VAE upcast, latents cast back
+    added = pipe.unet_kwargs
+    assert set(added) == {"text_embeds", "time_ids"}
+    assert added["text_embeds"].shape == (2, 1280) and added["text_embeds"][0, 0] == 3.0 and added["text_embeds"][1, 0] == 2.0
+    assert added["time_ids"].tolist() == [[32, 32, 0, 0, 32, 32]] * 2                   # (original, crop, target) x [neg, pos]
+    target = pipe.unet.up_blocks[:-1][1].attentions[0].transformer_blocks[1].attn1
+    assert target.stores[0] is q
+
+
+def test_pair_scoring_consumes_the_generator_in_the_reference_order():
+    """diffsim(A, B): VAE sample A, VAE sample B, noise A, noise B from ONE generator (diffsim/diffsim.py:109-113,
+    diffsim_pipeline.py:174-176); the cached path seeds each image afresh (VAE sample, noise), like diffsim_value."""
+    from diffsim_b200 import diffsim as D
+
+    calls = []
+
+    class T(D.Trunk):
+        def encode(self, image, img_size, generator):
+            calls.append(("vae", image, float(torch.rand(1, generator=generator))))
+            return image
+
+        def forward(self, latents, prompt, target_block, target_layer, target_step, generator):
+            calls.append(("noise", latents, float(torch.rand(1, generator=generator))))
+            return None
+
+    t = T()
+    g = torch.Generator().manual_seed(2334)
+    D._extract_pair(t, "A", "B", 512, "p", "up_blocks", 0, 600, g)
+    assert [c[:2] for c in calls] == [("vae", "A"), ("vae", "B"), ("noise", "A"), ("noise", "B")]
+    g2 = torch.Generator().manual_seed(2334)
+    expect = [float(torch.rand(1, generator=g2)) for _ in range(4)]
+    assert [c[2] for c in calls] == expect
+    calls.clear()
+    t.extract("B", 512, "p", "up_blocks", 0, 600, torch.Generator().manual_seed(2334))
+    assert [c[:2] for c in calls] == [("vae", "B"), ("noise", "B")] and calls[0][2] == expect[0]   # B's VAE draw differs from pair mode
+
+
+def test_scorers_refuse_to_run_without_a_trunk():
+    from diffsim_b200.diffsim import DiffSim, diffsim_DiT, diffsim_xl
+
+    for make in (lambda: DiffSim(torch.float32, "cpu"), lambda: diffsim_xl(torch.float32, "cpu"), lambda: diffsim_DiT(256, 600, "cpu")):
+        with pytest.raises(ValueError, match="needs a trunk"):
+            make()
+    with pytest.raises(ValueError, match="ckpt"):
+        diffsim_DiT(256, 600, "cpu", ckpt="DiT-XL-2-256x256.pt", trunk=DiffusersTrunk(_Pipe(), "cpu", torch.float32))
