@@ -381,6 +381,9 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const uint32_t d_tmem = tmem_base + kTmemS + h * kHalfKV;
 #pragma unroll
         for (int kc = 0; kc < C::D_PAD / 16; ++kc) {
+#if defined(DS_ABLATE) && (DS_ABLATE & 1)
+          if (kc >= C::D_PAD / 32) break;   // ABLATION: half of the QK MMAs
+#endif
           const int sub = kc / C::CPS, off = (kc % C::CPS) * 32;
           umma_f16_ss(d_tmem, q_desc0 + (uint64_t)((sub * C::Q_SUB_BYTES + off) >> 4),
                       k_desc + (uint64_t)((sub * C::KV_SUB_BYTES + off) >> 4), idesc_qk, kc > 0 ? 1u : 0u);
@@ -414,7 +417,11 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         // uniform-datapath instructions per step, about as long as the tensor core needs for the step itself
         if (ksteps == kHalfKV / 16) {
 #pragma unroll
+#if defined(DS_ABLATE) && (DS_ABLATE & 8)
+          for (int ks = 0; ks < kHalfKV / 32; ++ks) pv_step(ks);   // ABLATION: half of the PV MMAs
+#else
           for (int ks = 0; ks < kHalfKV / 16; ++ks) pv_step(ks);
+#endif
         } else {
 #pragma unroll 1
           for (int ks = 0; ks < ksteps; ++ks) pv_step(ks);
@@ -472,8 +479,13 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         DS_TRACE_EV(32 + h);
         tc_fence_after_sync();
         uint32_t v[32];
+#if defined(DS_ABLATE) && (DS_ABLATE & 16)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint((float)((w + j + lane) & 15));   // ABLATION: S is not read
+#else
         tmem_ld_x32(s_col + h * kHalfKV, v);   // also when nv == 0: stale columns, never used
         tmem_wait_ld();
+#endif
         // ragged tail (rare): columns past the kv length hold stale data, possibly NaN -- overwrite them with -inf once,
         // so that the common path below carries no per-column selects (-inf is neutral for the maximum and
         // exp2(-inf * scale - m) = 0; the host guarantees scale > 0)
@@ -499,9 +511,13 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         float* mx = sMax + (w & 1) * 512;
         mx[qtr * 128 + row] = m;
         DS_TRACE_EV(34 + h);
+#if defined(DS_ABLATE) && (DS_ABLATE & 64)
+        const float Mh = m;   // ABLATION: no exchange of the row maximum
+#else
         named_bar_sync(1 + quad, 128);   // the four warps of this TMEM quadrant (= of this scheduler) hold the row
         DS_TRACE_EV(36 + h);
         const float Mh = fmaxf(fmaxf(mx[row], mx[128 + row]), fmaxf(mx[256 + row], mx[384 + row]));
+#endif
         // Lazy running maximum: the first half of the item fixes the row's reference m_run; a later half keeps it and
         // simply lets p = exp2(s - m_run) grow -- up to 2^14 for fp16 P, 2^30 for bf16 -- which 16-bit P and the fp32
         // accumulators hold without loss (the offset cancels in O / l).  Only beyond that does the reference move, which
@@ -546,15 +562,26 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             // the MUFU pipe (16 ex2 / clk / SM) is what bounds this phase: every kPolyStride-th pair is evaluated on the
             // FMA pipe instead
             constexpr int kPolyStride = C::POLY_STRIDE;
+#if defined(DS_ABLATE) && (DS_ABLATE & 2)
+            e0 = x0; e1 = x1;   // ABLATION: no exponentials
+#else
             if (kPolyStride > 0 && ((j >> 1) % (kPolyStride > 0 ? kPolyStride : 1)) == 0) {
               exp2_poly_f2(x0, x1, e0, e1);
             } else {
               e0 = fast_exp2(x0);
               e1 = fast_exp2(x1);
             }
+#endif
             pk[j >> 1] = pack2<kBf16>(e0, e1);
           }
+#if defined(DS_ABLATE) && (DS_ABLATE & 32)
+          uint32_t x = 0;   // ABLATION: P is not written
+#pragma unroll
+          for (int j = 0; j < 16; ++j) x ^= pk[j];
+          if (x == 0x12345678u) tmem_st_x16(s_col + h * kHalfKV, pk);
+#else
           tmem_st_x16(s_col + h * kHalfKV, pk);
+#endif
         }
         tmem_wait_st();
         tc_fence_before_sync();
@@ -656,7 +683,11 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         } else if constexpr (MODE == ATTN_MODE_COS) {
           // unnormalised: dot = inv_l * sum o s, |Oc|^2 = inv_l^2 * sum o^2 (applied once per row below)
 #pragma unroll
+#if defined(DS_ABLATE) && (DS_ABLATE & 4)
+          for (int j = 0; j < 1; ++j) {   // ABLATION: 1/8 of the epilogue arithmetic
+#else
           for (int j = 0; j < 8; ++j) {
+#endif
             const float2 sv = unpack2<kBf16>(os[cur][j]);
             const uint64_t o2 = f2_pack_u(v[cur][2 * j], v[cur][2 * j + 1]);
             acc01 = f2_fma(o2, f2_pack(sv.x, sv.y), acc01);

@@ -42,6 +42,9 @@ struct GemmParams {
   uint32_t idesc2;          // CTA-pair kernel: M = 256
   int tma_store;            // CTA-pair kernel, 16-bit outputs: epilogue through TMA stores (GemmOutMaps)
   int use_pair;             // -1 automatic (set by launch_gemm_tn's callers that leave it 0-initialised: see below), 0, 1
+  // CTA-pair kernel only: operand given as a k-blocked copy [k block][rows_pad][64] (rows_pad a multiple of 256, value
+  // here; 0 = the row-major operand).  A TMA box is then one contiguous run instead of 128 row pieces 2*ld bytes apart.
+  int kblk_rows_a, kblk_rows_b;
   // GEMM_EPI_F32: part[split][M][N] fp32
   float* part;
   int64_t part_split_stride;
@@ -409,8 +412,10 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* a = smem + (size_t)stage * kG2StageBytes;
           if (leader) mbar_arrive_expect_tx(&full[stage], 2 * kG2StageBytes);
-          tma_load_2d_2cta(a, &map_a, &full[stage], kb * kGBK, tm * kG2BM + (int)rank * kGBM);
-          tma_load_2d_2cta(a + kGABytes, &map_b, &full[stage], kb * kGBK, tn * kGBN + (int)rank * (kGBN / 2));
+          tma_load_2d_2cta(a, &map_a, &full[stage], p.kblk_rows_a ? 0 : kb * kGBK,
+                           kb * p.kblk_rows_a + tm * kG2BM + (int)rank * kGBM);
+          tma_load_2d_2cta(a + kGABytes, &map_b, &full[stage], p.kblk_rows_b ? 0 : kb * kGBK,
+                           kb * p.kblk_rows_b + tn * kGBN + (int)rank * (kGBN / 2));
           if (++stage == kG2Stages) {
             stage = 0;
             phase ^= 1;
@@ -497,21 +502,38 @@ static int launch_gemm_tn(const void* a, int64_t M, int64_t lda, const void* b, 
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
     uint64_t str[1] = {(uint64_t)lda * 2};
     uint32_t box[2] = {(uint32_t)kGBK, (uint32_t)kGBM};
-    if ((rc = encode_tensor_map(&map_a, dtype, 2, a, dims, str, box, 128)) != DS_OK) return rc;
+    if (!p.kblk_rows_a && (rc = encode_tensor_map(&map_a, dtype, 2, a, dims, str, box, 128)) != DS_OK) return rc;
     uint64_t dimsb[2] = {(uint64_t)K, (uint64_t)N};
     uint64_t strb[1] = {(uint64_t)ldb * 2};
     uint32_t boxb[2] = {(uint32_t)kGBK, (uint32_t)kGBN};
-    if ((rc = encode_tensor_map(&map_b, dtype, 2, b, dimsb, strb, boxb, 128)) != DS_OK) return rc;
+    if (!p.kblk_rows_b && (rc = encode_tensor_map(&map_b, dtype, 2, b, dimsb, strb, boxb, 128)) != DS_OK) return rc;
   }
   p.M = (int)M;
   p.N = (int)N;
   // CTA pairs (256 x 256 tiles) when there are enough of them to fill the 74 clusters; small problems keep the 1-CTA shape
   const bool pair = gemm_use_pair(M, N, p.splits, p.use_pair);
+  if ((p.kblk_rows_a || p.kblk_rows_b) && !pair) return fail(DS_ERR_INVALID, "gemm: k-blocked operands need the CTA-pair kernel");
   if (pair) {
     uint64_t dimsb2[2] = {(uint64_t)K, (uint64_t)N};
     uint64_t strb2[1] = {(uint64_t)ldb * 2};
     uint32_t boxb2[2] = {(uint32_t)kGBK, (uint32_t)(kGBN / 2)};
-    if ((rc = encode_tensor_map(&map_b, dtype, 2, b, dimsb2, strb2, boxb2, 128)) != DS_OK) return rc;
+    if (!p.kblk_rows_b && (rc = encode_tensor_map(&map_b, dtype, 2, b, dimsb2, strb2, boxb2, 128)) != DS_OK) return rc;
+    // k-blocked operands: a 2-D view [k blocks * rows_pad][64], row pitch 128 bytes
+    const uint64_t kbt = (uint64_t)((K + kGBK - 1) / kGBK);
+    if (p.kblk_rows_a) {
+      uint64_t d[2] = {(uint64_t)kGBK, kbt * (uint64_t)p.kblk_rows_a};
+      uint64_t s1[1] = {(uint64_t)kGBK * 2};
+      uint32_t bx[2] = {(uint32_t)kGBK, (uint32_t)kGBM};
+      if (kbt * (uint64_t)p.kblk_rows_a > (uint64_t)INT32_MAX) return fail(DS_ERR_INVALID, "gemm: k-blocked operand too large");
+      if ((rc = encode_tensor_map(&map_a, dtype, 2, a, d, s1, bx, 128)) != DS_OK) return rc;
+    }
+    if (p.kblk_rows_b) {
+      uint64_t d[2] = {(uint64_t)kGBK, kbt * (uint64_t)p.kblk_rows_b};
+      uint64_t s1[1] = {(uint64_t)kGBK * 2};
+      uint32_t bx[2] = {(uint32_t)kGBK, (uint32_t)(kGBN / 2)};
+      if (kbt * (uint64_t)p.kblk_rows_b > (uint64_t)INT32_MAX) return fail(DS_ERR_INVALID, "gemm: k-blocked operand too large");
+      if ((rc = encode_tensor_map(&map_b, dtype, 2, b, d, s1, bx, 128)) != DS_OK) return rc;
+    }
     p.tiles_m = (int)((M + kG2BM - 1) / kG2BM);
     p.tiles_n = (int)((N + kGBN - 1) / kGBN);
     p.kb_total = (int)((K + kGBK - 1) / kGBK);

@@ -25,10 +25,13 @@ namespace ds {
 constexpr int kStatThreads = 256;
 constexpr int kStatMaxChunks = 64;
 
+// With `blocked` (may be null) the pass also writes the k-blocked copy the CTA-pair GEMM reads: element (row, e) goes to
+// blocked[((e / 64) * rows_pad + row) * 64 + e % 64], the tail of the last k block is zero-filled (rows >= n of a block are
+// never written: they only feed output rows the GEMM epilogue drops).  chunk_elems is a multiple of 64.
 template <typename T>
 __global__ void __launch_bounds__(kStatThreads)
 row_stats_kernel(const T* __restrict__ x, int64_t ld, int64_t L, int chunks, int64_t chunk_elems,
-                 float* __restrict__ partials /* [n][chunks][4] */) {
+                 float* __restrict__ partials /* [n][chunks][4] */, T* __restrict__ blocked, int64_t rows_pad) {
   const int64_t row = blockIdx.x / chunks;
   const int chunk = blockIdx.x % chunks;
   const T* xp = x + row * ld;
@@ -37,8 +40,10 @@ row_stats_kernel(const T* __restrict__ x, int64_t ld, int64_t L, int chunks, int
   float s = 0.f, ss = 0.f, mn = FLT_MAX, mx = -FLT_MAX;
   const int64_t nvec = (e1 > e0) ? (e1 - e0) / 8 : 0;
   const uint4* xv = reinterpret_cast<const uint4*>(xp + e0);
+  auto blk = [&](int64_t e) -> T* { return blocked + (((e >> 6) * rows_pad + row) << 6) + (e & 63); };
   for (int64_t i = threadIdx.x; i < nvec; i += kStatThreads) {
     uint4 u = __ldg(xv + i);
+    if (blocked) *reinterpret_cast<uint4*>(blk(e0 + i * 8)) = u;
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -52,7 +57,12 @@ row_stats_kernel(const T* __restrict__ x, int64_t ld, int64_t L, int chunks, int
       mx = fmaxf(mx, fmaxf(f.x, f.y));
     }
   }
+  if (blocked && e1 == L) {   // the chunk that holds the end of the row: zero the rest of the last k block
+    const int64_t pad_end = (L + 63) & ~(int64_t)63;
+    for (int64_t e = L + threadIdx.x; e < pad_end; e += kStatThreads) *blk(e) = T(0.f);
+  }
   for (int64_t e = e0 + nvec * 8 + threadIdx.x; e < e1; e += kStatThreads) {
+    if (blocked) *blk(e) = xp[e];
     float f;
     if constexpr (std::is_same<T, __nv_bfloat16>::value) f = __bfloat162float(xp[e]);
     else f = __half2float(xp[e]);
@@ -142,12 +152,15 @@ __global__ void simmat_finish_kernel(const float* __restrict__ part, int splits,
 }
 
 static int g_simmat_max_kb = 256;   // ds_debug_set_simmat_max_kb (A/B)
+static int g_simmat_blocked = -1;   // ds_debug_set_simmat_blocked: -1 automatic, 0 never, 1 whenever the pair kernel runs
 
 struct SimmatPlan {
   int tiles_m, tiles_n, kb_total, splits, kb_per_split;
   int pair;   // 1: CTA-pair kernel (256 x 256 tiles, 74 clusters)
   int stat_chunks;
   int64_t stat_chunk_elems;
+  int blocked;   // 1: the statistics pass also writes k-blocked operand copies and the GEMM reads those
+  int64_t rows_pad, cols_pad, kb64;   // extents of the k-blocked copies
 };
 
 static SimmatPlan simmat_plan(int64_t n_rows, int64_t n_cols, int64_t L, bool sym = false) {
@@ -190,6 +203,17 @@ static SimmatPlan simmat_plan(int64_t n_rows, int64_t n_cols, int64_t L, bool sy
   }
   p.kb_per_split = (p.kb_total + best_s - 1) / best_s;
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  // k-blocked operand copies: worth their extra HBM pass when an operand is far larger than the L2 -- the row-major TMA
+  // boxes (256 row pieces, 2 * ld bytes apart) then miss the L2 on 55% of the requests although the tiles that share a
+  // row block run at the same time; measured (profiles/r2_simmat_experiments.txt): 2032 x 655 360 (2.7 GB) 3.9 -> 3.35 ms,
+  // 2032 x 163 840 (0.67 GB) 0.68 -> 0.79 ms.  Writing the copy in stages UNDER the GEMM of the previous stage is slower than
+  // back to back (3.8 ms: the copy's stream of writes evicts the GEMM's L2 working set)
+  p.rows_pad = (n_rows + 255) / 256 * 256;
+  p.cols_pad = (n_cols + 255) / 256 * 256;
+  p.kb64 = (L + 63) / 64;
+  const bool big = (double)(n_rows > n_cols ? n_rows : n_cols) * (double)L * 2.0 >= 1536.0 * 1024 * 1024;
+  p.blocked = (p.pair && g_simmat_blocked != 0 && (big || g_simmat_blocked > 0)) ? 1 : 0;
+  if (p.kb64 * (p.rows_pad > p.cols_pad ? p.rows_pad : p.cols_pad) > (int64_t)INT32_MAX) p.blocked = 0;
   const int64_t quantum = 8 * kStatThreads;
   int64_t c = (L + 65535) / 65536;
   if (c > kStatMaxChunks) c = kStatMaxChunks;
@@ -204,6 +228,11 @@ static SimmatPlan simmat_plan(int64_t n_rows, int64_t n_cols, int64_t L, bool sy
 }  // namespace ds
 
 extern "C" {
+
+int ds_debug_set_simmat_blocked(int mode) {
+  if (mode >= -1 && mode <= 1) ds::g_simmat_blocked = mode;
+  return ds::g_simmat_blocked;
+}
 
 int ds_debug_set_simmat_max_kb(int kb) {
   if (kb >= 8) ds::g_simmat_max_kb = kb;
@@ -222,6 +251,7 @@ size_t ds_simmat_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t L) {
   b += align_up((size_t)p.splits * n_rows * n_cols * sizeof(float), 256);
   b += align_up((size_t)(n_rows + n_cols) * p.stat_chunks * 4 * sizeof(float), 256);
   b += align_up((size_t)(n_rows + n_cols) * 4 * sizeof(double), 256);
+  if (p.blocked) b += align_up((size_t)p.kb64 * (p.rows_pad + p.cols_pad) * 64 * 2, 256) + 256;
   return b + 1024;
 }
 
@@ -248,26 +278,36 @@ int ds_simmat(const void* rows, int64_t n_rows, int64_t ld_rows, const void* col
   float* part = static_cast<float*>(w.take((size_t)p.splits * n_rows * n_cols * sizeof(float)));
   float* spart = static_cast<float*>(w.take((size_t)(n_rows + n_cols) * p.stat_chunks * 4 * sizeof(float)));
   double* stats = static_cast<double*>(w.take((size_t)(n_rows + n_cols) * 4 * sizeof(double)));
-  if (!part || !spart || !stats)
+  void* blk_r = nullptr;
+  void* blk_c = nullptr;
+  if (p.blocked) {
+    blk_r = w.take((size_t)p.kb64 * p.rows_pad * 64 * 2);
+    blk_c = sym ? blk_r : w.take((size_t)p.kb64 * p.cols_pad * 64 * 2);
+  }
+  if (!part || !spart || !stats || (p.blocked && (!blk_r || !blk_c)))
     return fail(DS_ERR_WORKSPACE, "ds_simmat: workspace too small (%zu given, need %zu)", ws_bytes,
                 ds_simmat_workspace_bytes(n_rows, n_cols, L));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-  // statistics pass
+  // statistics pass (+ the k-blocked copies)
   float* spart_c = spart + (size_t)n_rows * p.stat_chunks * 4;
   double* stats_c = sym ? stats : stats + (size_t)n_rows * 4;
   if (dtype == DS_F16) {
     row_stats_kernel<__half><<<(unsigned)(n_rows * p.stat_chunks), kStatThreads, 0, st>>>(
-        static_cast<const __half*>(rows), ld_rows, L, p.stat_chunks, p.stat_chunk_elems, spart);
+        static_cast<const __half*>(rows), ld_rows, L, p.stat_chunks, p.stat_chunk_elems, spart, static_cast<__half*>(blk_r),
+        p.rows_pad);
     if (!sym)
       row_stats_kernel<__half><<<(unsigned)(n_cols * p.stat_chunks), kStatThreads, 0, st>>>(
-          static_cast<const __half*>(cols), ld_cols, L, p.stat_chunks, p.stat_chunk_elems, spart_c);
+          static_cast<const __half*>(cols), ld_cols, L, p.stat_chunks, p.stat_chunk_elems, spart_c, static_cast<__half*>(blk_c),
+          p.cols_pad);
   } else {
     row_stats_kernel<__nv_bfloat16><<<(unsigned)(n_rows * p.stat_chunks), kStatThreads, 0, st>>>(
-        static_cast<const __nv_bfloat16*>(rows), ld_rows, L, p.stat_chunks, p.stat_chunk_elems, spart);
+        static_cast<const __nv_bfloat16*>(rows), ld_rows, L, p.stat_chunks, p.stat_chunk_elems, spart,
+        static_cast<__nv_bfloat16*>(blk_r), p.rows_pad);
     if (!sym)
       row_stats_kernel<__nv_bfloat16><<<(unsigned)(n_cols * p.stat_chunks), kStatThreads, 0, st>>>(
-          static_cast<const __nv_bfloat16*>(cols), ld_cols, L, p.stat_chunks, p.stat_chunk_elems, spart_c);
+          static_cast<const __nv_bfloat16*>(cols), ld_cols, L, p.stat_chunks, p.stat_chunk_elems, spart_c,
+          static_cast<__nv_bfloat16*>(blk_c), p.cols_pad);
   }
   DS_CUDA_TRY(cudaGetLastError());
   row_stats_finish_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, st>>>(spart, p.stat_chunks, n_rows, stats);
@@ -281,7 +321,13 @@ int ds_simmat(const void* rows, int64_t n_rows, int64_t ld_rows, const void* col
   gp.use_pair = p.pair;
   gp.part = part;
   gp.part_split_stride = (int64_t)n_rows * n_cols;
-  rc = launch_gemm_tn<GEMM_EPI_F32>(rows, n_rows, ld_rows, cols, n_cols, ld_cols, L, dtype, gp, st);
+  if (p.blocked) {
+    gp.kblk_rows_a = (int)p.rows_pad;
+    gp.kblk_rows_b = (int)p.cols_pad;
+    rc = launch_gemm_tn<GEMM_EPI_F32>(blk_r, n_rows, 64, blk_c, n_cols, 64, L, dtype, gp, st);
+  } else {
+    rc = launch_gemm_tn<GEMM_EPI_F32>(rows, n_rows, ld_rows, cols, n_cols, ld_cols, L, dtype, gp, st);
+  }
   if (rc != DS_OK) return rc;
 
   const int64_t fblocks = ((n_cols + 255) / 256) * n_rows;

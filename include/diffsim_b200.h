@@ -97,6 +97,10 @@ int ds_debug_set_gemm_variant(int variant);
  * Shorter ranges mean more partials (HBM traffic) but a smaller L2 working set and a shorter truncating accumulation
  * chain.  Returns the value in force. */
 int ds_debug_set_simmat_max_kb(int kb);
+/* Debug / A-B only: whether ds_simmat's statistics pass also writes k-blocked operand copies for the CTA-pair GEMM:
+ * -1 automatic (default: when the operands exceed 512 MB), 0 never, 1 whenever the pair kernel runs.  Returns the value
+ * in force. */
+int ds_debug_set_simmat_blocked(int mode);
 
 /* ---- K1: attention ------------------------------------------------------ */
 

@@ -335,6 +335,40 @@ def test_simmat(dtype, nr, nc, L):
     assert (ops.simmat(a, b, "cosine").diagonal().cpu() - pr).abs().max().item() < 1e-5
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("nr,nc,L", [(512, 512, 4096), (777, 520, 10008), (600, 1030, 200), (2032, 2032, 1024 + 8)])
+def test_simmat_k_blocked_operand_copies(dtype, nr, nc, L):
+    """Large operands go through k-blocked copies written by the statistics pass (automatic above 1.5 GB per operand; forced
+    here at test sizes).  Same MMAs in the same order: the result is bitwise that of the row-major path -- ragged row counts
+    (tiles overhanging the copy's padded rows), L with a partly filled last k block, self and rows x other."""
+    dev = _cuda()
+    from diffsim_b200 import _native, ops
+
+    lib = _native.load()
+    g = torch.Generator().manual_seed(nr * 3 + nc + L)
+    a = (torch.randn(nr, L, generator=g) * 0.5 + 0.1).to(dtype).to(dev)
+    b = (torch.randn(nc, L, generator=g) * 0.5 - 0.2).to(dtype).to(dev)
+    try:
+        out = {}
+        for blocked in (0, 1):
+            assert lib.ds_debug_set_simmat_blocked(blocked) == blocked
+            out[blocked] = [ops.simmat(a, b, "cosine"), ops.simmat(a, None, "minmax_cosine"), ops.simmat(b, None, "cosine")]
+    finally:
+        lib.ds_debug_set_simmat_blocked(-1)
+    for x, y in zip(out[0], out[1]):
+        assert torch.equal(x, y)
+    ref = O.simmat(a[:48].cpu(), b.cpu(), "cosine")
+    assert (out[1][0][:48].double().cpu() - ref).abs().max().item() < 2e-5
+    # a view with a leading dimension larger than L
+    wide = torch.zeros(nr, L + 24, dtype=dtype, device=dev)
+    wide[:, :L] = a
+    try:
+        lib.ds_debug_set_simmat_blocked(1)
+        assert torch.equal(ops.simmat(wide[:, :L], b, "cosine"), out[1][0])
+    finally:
+        lib.ds_debug_set_simmat_blocked(-1)
+
+
 def test_simmat_self_is_symmetric_with_unit_diagonal():
     dev = _cuda()
     from diffsim_b200 import ops
