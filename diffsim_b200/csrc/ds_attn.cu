@@ -110,6 +110,9 @@ struct AttnParams {
   // debug timeline (ds_debug_set_trace; compiled in only with -DDS_TRACE): [8 slots][cap] of (tag << 48 | clock)
   unsigned long long* trace;
   int trace_cap;
+  // 1: the kernel runs as clusters of two CTAs that work on the two q tiles (2j, 2j + 1) of the same (group, b, h) -- the
+  // same K/V sequence -- and load every K/V tile ONCE for both (TMA multicast, alternating which CTA issues a load)
+  int mc;
   unsigned long long* cycles;   // optional: CTA 0 stores its elapsed SM clocks here (ds_debug_set_trace(buf, cap): buf[8*cap])
 };
 
@@ -275,7 +278,7 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     mbar_init(o_empty, 256);
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
+      mbar_init(&kv_empty[s], p.mc ? 2 : 1);   // multicast: a slot is free once BOTH CTAs' MMAs have read it
     }
     fence_mbar_init();
   }
@@ -292,6 +295,7 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
+  if (p.mc) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast at them
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -302,15 +306,26 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       uint32_t phase = 0, sc = 0;
       // one ring stage = up to 128 kv rows (rows past the tensor end are zero-filled by TMA)
       DS_TRACE_DECL(0)
+      const uint32_t mc_rank = p.mc ? cluster_ctarank() : 0u;
+      uint32_t n_loads = 0;
       auto load_half = [&](const CUtensorMap* m, int img, int bb, int hh, int row0) {
         DS_TRACE_EV(1);
         mbar_wait(&kv_empty[stage], phase ^ 1);
         DS_TRACE_EV(2);
         uint8_t* dst = sRing + (size_t)stage * C::STAGE_BYTES;
         mbar_arrive_expect_tx(&kv_full[stage], C::STAGE_BYTES);
+        if (p.mc) {
+          // both CTAs walk the same K/V sequence: sub-tile s of load n is fetched by CTA (n + s) % 2 for both
 #pragma unroll
-        for (int s = 0; s < C::NSUB; ++s)
-          tma_load_5d(dst + s * C::KV_SUB_BYTES, m, &kv_full[stage], s * C::SUBW, row0, hh, bb, img);
+          for (int s = 0; s < C::NSUB; ++s)
+            if (((n_loads + s) & 1u) == mc_rank)
+              tma_load_5d_mc(dst + s * C::KV_SUB_BYTES, m, &kv_full[stage], s * C::SUBW, row0, hh, bb, img, (uint16_t)3);
+          ++n_loads;
+        } else {
+#pragma unroll
+          for (int s = 0; s < C::NSUB; ++s)
+            tma_load_5d(dst + s * C::KV_SUB_BYTES, m, &kv_full[stage], s * C::SUBW, row0, hh, bb, img);
+        }
         if (++stage == C::STAGES) {
           stage = 0;
           phase ^= 1;
@@ -388,7 +403,8 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           umma_f16_ss(d_tmem, q_desc0 + (uint64_t)((sub * C::Q_SUB_BYTES + off) >> 4),
                       k_desc + (uint64_t)((sub * C::KV_SUB_BYTES + off) >> 4), idesc_qk, kc > 0 ? 1u : 0u);
         }
-        umma_commit(&kv_empty[stage]);
+        if (p.mc) umma_commit_mc(&kv_empty[stage], (uint16_t)3);
+        else umma_commit(&kv_empty[stage]);
         advance();
         umma_commit(&s_full[h]);
         DS_TRACE_EV(14 + h);
@@ -426,7 +442,8 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll 1
           for (int ks = 0; ks < ksteps; ++ks) pv_step(ks);
         }
-        umma_commit(&kv_empty[stage]);
+        if (p.mc) umma_commit_mc(&kv_empty[stage], (uint16_t)3);
+        else umma_commit(&kv_empty[stage]);
         advance();
         if (h) ++pv_cntB; else ++pv_cntA;
         umma_commit(pv_half);
@@ -750,6 +767,7 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (p.mc) cluster_sync_all();   // the peer may still multicast into this CTA's ring / arrive on its barriers
   if (warp == kWarpMma) tmem_dealloc(tmem_base, kTmemCols);
   if (p.cycles && blockIdx.x == 0 && threadIdx.x == 0) *p.cycles = (unsigned long long)(clock64() - clk_start);
 }
@@ -952,6 +970,7 @@ static int make_map(CUtensorMap* m, const ds_tensor5& t, int subw, int rows) {
   return encode_tensor_map(m, t.dtype, 5, t.ptr, dims, strides, box, subw * 2);
 }
 
+static int g_attn_mc = -1;   // ds_debug_set_attn_mc: -1 automatic (on when the q tile count is even), 0 off
 static unsigned long long* g_trace_ptr = nullptr;
 static int g_trace_cap = 0;
 
@@ -967,7 +986,38 @@ static int launch_attn_one(const AttnLaunch& a, int grid, const CUtensorMap& mq,
   using C = AttnCfg<D>;
   DS_CUDA_TRY(cudaFuncSetAttribute(aas_attn_kernel<D, kBf16, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    C::SMEM_BYTES));
-  aas_attn_kernel<D, kBf16, MODE><<<grid, kAttnThreads, C::SMEM_BYTES, st>>>(mq, mks, mvs, mk, mv, a.p);
+  if (!a.p.mc) {
+    aas_attn_kernel<D, kBf16, MODE><<<grid, kAttnThreads, C::SMEM_BYTES, st>>>(mq, mks, mvs, mk, mv, a.p);
+    return DS_OK;
+  }
+  // clusters of two CTAs (the q tiles 2j, 2j + 1 of a stream pair share every K/V load).  The schedule is static, so the
+  // grid must not exceed what is co-resident: a GPC with an odd SM count cannot pair its last SM.
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3((unsigned)(grid & ~1));
+  cfg.blockDim = dim3(kAttnThreads);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  static int max_clusters[64] = {};
+  int dev = 0;
+  DS_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64) {
+    if (max_clusters[dev] == 0) {
+      int n = 0;
+      cudaLaunchConfig_t q = cfg;
+      q.gridDim = dim3((unsigned)(sm_count() & ~1));
+      DS_CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, aas_attn_kernel<D, kBf16, MODE>, &q));
+      max_clusters[dev] = n > 0 ? n : -1;
+    }
+    if (max_clusters[dev] > 0 && (int)cfg.gridDim.x > 2 * max_clusters[dev]) cfg.gridDim.x = 2 * max_clusters[dev];
+  }
+  DS_CUDA_TRY(cudaLaunchKernelEx(&cfg, aas_attn_kernel<D, kBf16, MODE>, mq, mks, mvs, mk, mv, a.p));
   return DS_OK;
 }
 
@@ -999,6 +1049,9 @@ static int launch_attn_d(const AttnLaunch& a, cudaStream_t st) {
   int grid = sm_count();
   if (n_streams < grid) grid = (int)n_streams;
   if (grid <= 0) return DS_OK;
+  // K/V multicast over CTA pairs needs the two q tiles of a pair to exist (q tile is the fastest stream index, so CTAs
+  // 2c and 2c + 1 hold q tiles 2j and 2j + 1 of the same (group, b, h) when n_qt and the grid are even)
+  const_cast<AttnLaunch&>(a).p.mc = (g_attn_mc != 0 && a.p.n_qt % 2 == 0 && grid >= 2) ? 1 : 0;
   profile_begin(st);
   int rc2 = DS_OK;
   if (a.q.dtype == DS_BF16) rc2 = launch_attn_mode<D, true>(a, grid, mq, mks, mvs, mk, mv, st);
@@ -1080,6 +1133,11 @@ int ds_debug_set_trace(void* dev_buf, int cap) {
 #else
   return 0;
 #endif
+}
+
+int ds_debug_set_attn_mc(int mode) {
+  if (mode >= -1 && mode <= 1) ds::g_attn_mc = mode;
+  return ds::g_attn_mc;
 }
 
 size_t ds_attn_fwd_workspace_bytes(ds_tensor4 q, ds_tensor4 k) {

@@ -343,6 +343,28 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
       ::"r"(smem_u32(bar)), "h"((uint16_t)3)
       : "memory");
 }
+// ---------------------------------------------------------------------------
+// Multicast inside a cluster of independent CTAs (cta_group::1 MMAs): one TMA load lands at the same shared-memory offset
+// of every CTA in cta_mask and completes transaction bytes on the mbarrier at the same offset of each; one L2 read serves
+// all of them.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_5d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                               int c3, int c4, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, "
+      "%5, %6, %7}], [%2], %8;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3), "r"(c4), "h"(cta_mask)
+      : "memory");
+}
+// arrive on the mbarrier at this offset in every CTA of cta_mask once this thread's issued MMAs have completed
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+
 // arrive on the LEADER's copy of a barrier (from either CTA of the pair)
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile(
