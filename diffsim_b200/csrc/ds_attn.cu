@@ -970,7 +970,9 @@ static int make_map(CUtensorMap* m, const ds_tensor5& t, int subw, int rows) {
   return encode_tensor_map(m, t.dtype, 5, t.ptr, dims, strides, box, subw * 2);
 }
 
-static int g_attn_mc = -1;   // ds_debug_set_attn_mc: -1 automatic (on when the q tile count is even), 0 off
+// ds_debug_set_attn_mc: -1 automatic (the N x N matrix only: +2-3% there, -1% sustained and +16% DRAM reads on pair / triplet
+// lists, profiles/r2_attn_experiments.txt section 8), 0 off, 1 on wherever the q tile count is even
+static int g_attn_mc = -1;
 static unsigned long long* g_trace_ptr = nullptr;
 static int g_trace_cap = 0;
 
@@ -978,6 +980,7 @@ struct AttnLaunch {
   ds_tensor5 q, ks, vs, k, v;
   AttnParams p;
   int mode;   // ATTN_MODE_*
+  int prefer_mc = 0;   // the caller's work list has many kv images per query image: share K/V loads over CTA pairs
 };
 
 template <int D, bool kBf16, int MODE>
@@ -1051,7 +1054,8 @@ static int launch_attn_d(const AttnLaunch& a, cudaStream_t st) {
   if (grid <= 0) return DS_OK;
   // K/V multicast over CTA pairs needs the two q tiles of a pair to exist (q tile is the fastest stream index, so CTAs
   // 2c and 2c + 1 hold q tiles 2j and 2j + 1 of the same (group, b, h) when n_qt and the grid are even)
-  const_cast<AttnLaunch&>(a).p.mc = (g_attn_mc != 0 && a.p.n_qt % 2 == 0 && grid >= 2) ? 1 : 0;
+  const bool want_mc = g_attn_mc == 1 || (g_attn_mc < 0 && a.prefer_mc);
+  const_cast<AttnLaunch&>(a).p.mc = (want_mc && a.p.n_qt % 2 == 0 && grid >= 2) ? 1 : 0;
   profile_begin(st);
   int rc2 = DS_OK;
   if (a.q.dtype == DS_BF16) rc2 = launch_attn_mode<D, true>(a, grid, mq, mks, mvs, mk, mv, st);
@@ -1395,6 +1399,7 @@ int ds_aas_matrix(ds_tensor5 q, ds_tensor5 k_self, ds_tensor5 v_self, ds_tensor5
   a.p.n_groups = (int)G;
   a.p.self_first = 1;
   a.mode = (mode == DS_SIM_MSE) ? ATTN_MODE_MSE : ATTN_MODE_COS;
+  a.prefer_mc = 1;
   a.p.part = part;
   a.p.out = nullptr;
   a.p.out_sb = a.p.out_sh = a.p.out_ss = 0;

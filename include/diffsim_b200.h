@@ -98,8 +98,8 @@ int ds_debug_set_gemm_variant(int variant);
  * chain.  Returns the value in force. */
 int ds_debug_set_simmat_max_kb(int kb);
 /* Debug / A-B only: K1's K/V multicast over CTA pairs (clusters of two CTAs on the q tiles 2j, 2j + 1 of one (group, b, h),
- * every K/V tile read from L2 once for both): -1 automatic (default: on whenever the q tile count is even), 0 off.
- * Returns the value in force. */
+ * every K/V tile read from L2 once for both): -1 automatic (default: ds_aas_matrix only, where it measures +2-3%), 0 off,
+ * 1 on in every call whose q tile count is even.  Returns the value in force. */
 int ds_debug_set_attn_mc(int mode);
 /* Debug / A-B only: whether ds_simmat's statistics pass also writes k-blocked operand copies for the CTA-pair GEMM:
  * -1 automatic (default: when the operands exceed 512 MB), 0 never, 1 whenever the pair kernel runs.  Returns the value

@@ -264,6 +264,39 @@ def test_matrix_matches_oracle_and_row_blocks_are_bitwise_identical():
         assert s == pytest.approx(0.5 * (dm[a, b].item() + dm[b, a].item()), rel=1e-6)
 
 
+@pytest.mark.parametrize("shape,dtype", [((2, 8, 256, 160), torch.float16), ((1, 3, 512, 64), torch.bfloat16),
+                                         ((2, 2, 256, 72), torch.float16), ((1, 2, 1024, 40), torch.float16)])
+def test_kv_multicast_over_cta_pairs_is_bitwise_neutral(shape, dtype):
+    """K1 may run as clusters of two CTAs (the q tiles 2j, 2j + 1 of one (group, b, h)) that fetch every K/V tile once for both
+    with TMA multicast; automatic for the N x N matrix, forced here for pair and triplet lists too.  Same arithmetic per
+    CTA: every score is bitwise that of the unclustered launch."""
+    dev = _cuda()
+    from diffsim_b200 import _native, ops, synth
+
+    lib = _native.load()
+    m = synth.SynthModel(*shape, seed=2334)
+    images, labels = synth.make_styles(m, 4, 3, dtype, seed=11)
+    q, k, v = synth.stack_cache(images, dev)
+    pairs = [(0, 1), (2, 7), (5, 5), (11, 3), (4, 9)]
+    trips = torch.tensor([[0, 1, 2], [3, 4, 5], [6, 7, 8], [9, 10, 11], [1, 5, 9]], dtype=torch.int32, device=dev)
+    out = {}
+    try:
+        for mc in (0, 1):
+            assert lib.ds_debug_set_attn_mc(mc) == mc
+            t = ops.aas_triplets(q, k, v, trips, "cosine")
+            out[mc] = [ops.aas_pairs(q, k, v, pairs, "cosine"), ops.aas_pairs(q, k, v, pairs, "mse"),
+                       ops.aas_matrix(q, k, v, k, v, "cosine"), ops.aas_matrix(q[:5], k[:5], v[:5], k, v, "mse")]
+            out[mc] += [x for x in (t if isinstance(t, (tuple, list)) else [t]) if torch.is_tensor(x)]
+    finally:
+        lib.ds_debug_set_attn_mc(-1)
+    assert len(out[0]) == len(out[1]) >= 5
+    for a, b in zip(out[0], out[1]):
+        assert torch.equal(a, b)
+    assert torch.equal(ops.aas_matrix(q, k, v, k, v, "cosine"), out[0][2])     # automatic mode (multicast on for the matrix)
+    ref = torch.tensor([O.aas_pair_score(*images[a], *images[b], mode="cosine") for a, b in pairs], dtype=torch.float64)
+    assert ((out[1][0].cpu().double() - ref).abs() / ref.abs().clamp_min(1e-9)).max().item() < REL_16BIT
+
+
 # ------------------------------------------------------------------------------------------------------
 # K2 / K3
 # ------------------------------------------------------------------------------------------------------
