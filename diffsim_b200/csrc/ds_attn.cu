@@ -339,12 +339,14 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         // and PV_A(u-1) must not queue behind it.
         if (have_prev) load_half(prev.self ? &map_vs : &map_v, prev.img, prev.b, prev.h, prev.kv0);
         if (G.first_of_stream) {
+          DS_TRACE_EV(3);
           mbar_wait(q_empty, (sc & 1) ^ 1);
           mbar_arrive_expect_tx(q_full, C::Q_BYTES);
 #pragma unroll
           for (int s = 0; s < C::NSUB; ++s)
             tma_load_5d(sQ + s * C::Q_SUB_BYTES, &map_q, q_full, s * C::SUBW, G.qt * kBlockQ, G.h, G.b, G.qi);
           ++sc;
+          DS_TRACE_EV(4);
         }
         load_half(G.self ? &map_ks : &map_k, G.img, G.b, G.h, G.kv0);
         if (have_prev && prev.rowsB) load_half(prev.self ? &map_vs : &map_v, prev.img, prev.b, prev.h, prev.kv0 + kHalfKV);
@@ -386,8 +388,10 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         DS_TRACE_EV(10 + h);
         const uint32_t idesc_qk = umma_idesc_f16(fmt, kBlockQ, (uint32_t)((rows + 15) & ~15), 0, 0);
         if (h == 0 && G.first_of_stream) {
+          DS_TRACE_EV(17);
           mbar_wait(q_full, sc & 1);
           ++sc;
+          DS_TRACE_EV(18);
         }
         mbar_wait(&kv_full[stage], phase);
         DS_TRACE_EV(12 + h);

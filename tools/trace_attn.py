@@ -7,8 +7,8 @@ import torch
 from diffsim_b200 import ops, synth, _native as N
 
 CAP = 4096
-B, H, S, D = 2, 8, 256, 160
-n_img = 768
+B, H, S, D = (int(x) for x in os.environ.get("TR_SHAPE", "2,8,256,160").split(","))
+n_img = int(os.environ.get("TR_IMAGES", "768"))
 q, k, v = synth.device_cache(B, H, S, D, n_img, torch.float16, "cuda")
 pairs = torch.tensor([(3 * t, 3 * t + 1) for t in range(n_img // 3)] + [(3 * t, 3 * t + 2) for t in range(n_img // 3)],
                      dtype=torch.int32, device="cuda")
@@ -22,9 +22,13 @@ ops.aas_pairs(q, k, v, pairs, "cosine")
 torch.cuda.synchronize()
 lib.ds_debug_set_trace(None, 0)
 t = buf.cpu().view(8, CAP)
-names = {1: "prod wait kv_empty", 2: "prod got slot", 10: "mma qk begin", 11: "mma qk s_free ok", 12: "mma qk kv ready", 13: "mma qk mmas issued", 14: "mma qk committed",
-         20: "mma pv begin", 22: "mma pv p_full ok", 23: "mma pv o_empty ok", 24: "mma pv kv ready", 25: "mma pv mmas issued", 26: "mma pv committed",
-         30: "sm wait s_full", 32: "sm got S", 34: "sm max written", 36: "sm bar passed", 38: "sm arrived p_full",
+names = {1: "prod wait kv_empty", 2: "prod got slot", 3: "prod wait q_empty", 4: "prod Q issued",
+         10: "mma qkA begin", 11: "mma qkB begin", 12: "mma qkA kv ready", 13: "mma qkB kv ready", 14: "mma qkA committed",
+         15: "mma qkB committed", 17: "mma wait q_full", 18: "mma got Q",
+         20: "mma pvA begin", 21: "mma pvB begin", 22: "mma pvA p_full ok", 23: "mma pvB p_full ok", 24: "mma pvA o_empty + kv ready",
+         25: "mma pvB kv ready", 26: "mma pvA committed", 27: "mma pvB committed",
+         30: "sm wait s_full A", 31: "sm wait s_full B", 32: "sm got S_A", 33: "sm got S_B", 34: "sm max A written", 35: "sm max B written",
+         36: "sm bar A passed", 37: "sm bar B passed", 38: "sm arrived p_full A", 39: "sm arrived p_full B",
          40: "epi o_full", 42: "epi released O", 41: "epi done"}
 ev = []
 for slot in range(8):
