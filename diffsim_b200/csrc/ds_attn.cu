@@ -499,6 +499,9 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         mbar_wait(&s_full[h], (h ? cntB : cntA) & 1);
         DS_TRACE_EV(32 + h);
         tc_fence_after_sync();
+#if defined(DS_ABLATE) && (DS_ABLATE & 256)
+        mbar_arrive(&p_full[h]);   // ABLATION: P is declared ready at once -- the MMA side never waits for the softmax
+#endif
         uint32_t v[32];
 #if defined(DS_ABLATE) && (DS_ABLATE & 16)
 #pragma unroll
@@ -507,6 +510,7 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         tmem_ld_x32(s_col + h * kHalfKV, v);   // also when nv == 0: stale columns, never used
         tmem_wait_ld();
 #endif
+        DS_TRACE_EV(48 + h);
         // ragged tail (rare): columns past the kv length hold stale data, possibly NaN -- overwrite them with -inf once,
         // so that the common path below carries no per-column selects (-inf is neutral for the maximum and
         // exp2(-inf * scale - m) = 0; the host guarantees scale > 0)
@@ -604,9 +608,13 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           tmem_st_x16(s_col + h * kHalfKV, pk);
 #endif
         }
+        DS_TRACE_EV(44 + h);
         tmem_wait_st();
+        DS_TRACE_EV(46 + h);
         tc_fence_before_sync();
+#if !(defined(DS_ABLATE) && (DS_ABLATE & 256))
         mbar_arrive(&p_full[h]);
+#endif
         DS_TRACE_EV(38 + h);
         if (h) ++cntB; else ++cntA;
       }
@@ -977,6 +985,7 @@ static int make_map(CUtensorMap* m, const ds_tensor5& t, int subw, int rows) {
 // ds_debug_set_attn_mc: -1 automatic (the N x N matrix only: +2-3% there, -1% sustained and +16% DRAM reads on pair / triplet
 // lists, profiles/r2_attn_experiments.txt section 8), 0 off, 1 on wherever the q tile count is even
 static int g_attn_mc = -1;
+static int g_attn_grid = 0;   // ds_debug_set_attn_grid: > 0 caps K1's persistent grid (load experiments); 0 = one CTA per SM
 static unsigned long long* g_trace_ptr = nullptr;
 static int g_trace_cap = 0;
 
@@ -1055,6 +1064,7 @@ static int launch_attn_d(const AttnLaunch& a, cudaStream_t st) {
   const_cast<AttnLaunch&>(a).p.cycles = g_trace_ptr ? g_trace_ptr + (size_t)8 * g_trace_cap : nullptr;
   int grid = sm_count();
   if (n_streams < grid) grid = (int)n_streams;
+  if (g_attn_grid > 0 && g_attn_grid < grid) grid = g_attn_grid;
   if (grid <= 0) return DS_OK;
   // K/V multicast over CTA pairs needs the two q tiles of a pair to exist (q tile is the fastest stream index, so CTAs
   // 2c and 2c + 1 hold q tiles 2j and 2j + 1 of the same (group, b, h) when n_qt and the grid are even)
@@ -1141,6 +1151,11 @@ int ds_debug_set_trace(void* dev_buf, int cap) {
 #else
   return 0;
 #endif
+}
+
+int ds_debug_set_attn_grid(int ctas) {
+  if (ctas >= 0) ds::g_attn_grid = ctas;
+  return ds::g_attn_grid;
 }
 
 int ds_debug_set_attn_mc(int mode) {

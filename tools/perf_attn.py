@@ -17,6 +17,9 @@ def child():
     trips = torch.arange(3 * T, dtype=torch.int32, device="cuda").view(T, 3)
     cyc = torch.zeros(8 * 4 + 1, dtype=torch.int64, device="cuda")
     lib = N.load()
+    grid = int(os.environ.get("PERF_GRID", "148"))
+    if grid != 148:
+        lib.ds_debug_set_attn_grid(grid)
     out = []
     for name, fn, attn in (("pairs", lambda: ops.aas_pairs(q, k, v, pairs, "cosine"), 4 * pairs.shape[0]),
                            ("triplets", lambda: ops.aas_triplets(q, k, v, trips, "cosine"), 7 * T)):
@@ -34,7 +37,7 @@ def child():
         fn()
         torch.cuda.synchronize()
         lib.ds_debug_set_trace(None, 0)
-        items = attn * B * H * (S // 128) / 148
+        items = attn * B * H * (S // 128) / grid
         tf = attn * 4 * B * H * S * S * D / ms / 1e9
         out.append(f"{name}: {int(cyc[-1]) / items:.0f} clk/item, {ms:.3f} ms, {tf:.0f} TFLOP/s, {int(cyc[-1]) / ms / 1e6:.2f} GHz")
     print(" | ".join(out))

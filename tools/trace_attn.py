@@ -14,6 +14,8 @@ pairs = torch.tensor([(3 * t, 3 * t + 1) for t in range(n_img // 3)] + [(3 * t, 
                      dtype=torch.int32, device="cuda")
 buf = torch.zeros(8 * CAP, dtype=torch.int64, device="cuda")
 lib = N.load()
+if os.environ.get("TR_GRID"):
+    lib.ds_debug_set_attn_grid(int(os.environ["TR_GRID"]))
 ops.aas_pairs(q, k, v, pairs, "cosine")
 torch.cuda.synchronize()
 on = lib.ds_debug_set_trace(buf.data_ptr(), CAP)
@@ -29,6 +31,8 @@ names = {1: "prod wait kv_empty", 2: "prod got slot", 3: "prod wait q_empty", 4:
          25: "mma pvB kv ready", 26: "mma pvA committed", 27: "mma pvB committed",
          30: "sm wait s_full A", 31: "sm wait s_full B", 32: "sm got S_A", 33: "sm got S_B", 34: "sm max A written", 35: "sm max B written",
          36: "sm bar A passed", 37: "sm bar B passed", 38: "sm arrived p_full A", 39: "sm arrived p_full B",
+         44: "sm P_A stored (issued)", 45: "sm P_B stored (issued)", 46: "sm st A complete", 47: "sm st B complete",
+         48: "sm S_A in registers", 49: "sm S_B in registers",
          40: "epi o_full", 42: "epi released O", 41: "epi done"}
 ev = []
 for slot in range(8):
