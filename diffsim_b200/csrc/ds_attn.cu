@@ -393,7 +393,7 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           ++sc;
           DS_TRACE_EV(18);
         }
-        mbar_wait(&kv_full[stage], phase);
+        if (!mbar_test_wait(&kv_full[stage], phase)) mbar_wait(&kv_full[stage], phase);
         DS_TRACE_EV(12 + h);
         tc_fence_after_sync();
         const uint64_t k_desc = k_desc0 + (uint64_t)((stage * C::STAGE_BYTES) >> 4);
@@ -418,10 +418,20 @@ aas_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       auto issue_pv = [&](const LiteGroup& G, int h) {
         const int rows = h ? G.rowsB : G.rowsA;
         DS_TRACE_EV(20 + h);
-        mbar_wait(&p_full[h], (h ? pv_cntB : pv_cntA) & 1);
-        DS_TRACE_EV(22 + h);
-        if (h == 0 && G.first_of_item) mbar_wait(o_empty, (items_pv & 1) ^ 1);
-        mbar_wait(&kv_full[stage], phase);
+        {
+          // the tensor queue hides only ~175 clk of this thread's time between two bursts (tools/ubench/ubench_k1_mma.cu), and
+          // a wait costs 100+ clk even on a completed barrier: probe all barriers of the burst at once (the probes' latencies
+          // overlap), then wait properly only on those that were not complete (-80 clk per item)
+          const uint32_t par_p = (h ? pv_cntB : pv_cntA) & 1;
+          const bool need_o = h == 0 && G.first_of_item;
+          const bool ok_p = mbar_test_wait(&p_full[h], par_p);
+          const bool ok_k = mbar_test_wait(&kv_full[stage], phase);
+          const bool ok_o = need_o ? mbar_test_wait(o_empty, (items_pv & 1) ^ 1) : true;
+          if (!ok_p) mbar_wait(&p_full[h], par_p);
+          DS_TRACE_EV(22 + h);
+          if (!ok_o) mbar_wait(o_empty, (items_pv & 1) ^ 1);
+          if (!ok_k) mbar_wait(&kv_full[stage], phase);
+        }
         DS_TRACE_EV(24 + h);
         tc_fence_after_sync();
         const uint64_t v_desc = v_desc0 + (uint64_t)((stage * C::STAGE_BYTES) >> 4);

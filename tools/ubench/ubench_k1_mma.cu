@@ -18,7 +18,15 @@ constexpr int kQBytes = kNSub * 128 * kSubBytes;            // 40 KB
 constexpr int kTileBytes = kNSub * 128 * kSubBytes;         // one K or V half: 40 KB
 constexpr int kSmem = 1024 + kQBytes + 4 * kTileBytes + 2048 + 256;
 
-__global__ void __launch_bounds__(128, 1) k1_mma_kernel(int mode, int items, long long* clk_out, float* sink) {
+__device__ __forceinline__ void spin(int clk) {
+  if (clk <= 0) return;
+  const long long t = clock64();
+  while (clock64() - t < clk) {}
+}
+
+// gap: SM clocks the issuing thread idles before each of the four bursts of an item (mode 0 only) -- how much per-burst
+// overhead of the issuing thread does the tensor queue hide?
+__global__ void __launch_bounds__(128, 1) k1_mma_kernel(int mode, int items, long long* clk_out, float* sink, int gap) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
@@ -104,7 +112,7 @@ __global__ void __launch_bounds__(128, 1) k1_mma_kernel(int mode, int items, lon
       if (it >= 2) mbar_wait(&bar[it & 1], ((it - 2) >> 1) & 1);
       tc_fence_after_sync();
       switch (mode) {
-        case 0: pv(0, true); qk(0); pv(1, true); qk(1); break;
+        case 0: spin(gap); pv(0, true); spin(gap); qk(0); spin(gap); pv(1, true); spin(gap); qk(1); break;
         case 1: qk(0); qk(1); break;
         case 2: pv(0, false); pv(1, false); break;
         case 3: pv(0, true); pv(1, true); break;
@@ -150,12 +158,12 @@ int main(int argc, char** argv) {
   for (int rep = 0; rep < reps; ++rep)
     for (int mode = 0; mode < 6; ++mode) {
       const int items = 200000;   // ~0.3 - 0.6 s per launch: long enough for the power governor to settle
-      k1_mma_kernel<<<sms, 128, kSmem>>>(mode, 2000, clk, sink);
+      k1_mma_kernel<<<sms, 128, kSmem>>>(mode, 2000, clk, sink, 0);
       cudaEvent_t e0, e1;
       cudaEventCreate(&e0);
       cudaEventCreate(&e1);
       cudaEventRecord(e0);
-      k1_mma_kernel<<<sms, 128, kSmem>>>(mode, items, clk, sink);
+      k1_mma_kernel<<<sms, 128, kSmem>>>(mode, items, clk, sink, 0);
       cudaEventRecord(e1);
       cudaError_t err = cudaDeviceSynchronize();
       if (err != cudaSuccess) {
@@ -171,5 +179,15 @@ int main(int argc, char** argv) {
              useful[mode] * items * sms / (ms * 1e-3) / 1e12, (double)c / (ms * 1e6));
       fflush(stdout);
     }
+  // queue depth probe: the K1 mix with the issuing thread idling `gap` clocks before every burst
+  for (int gap : {0, 50, 100, 200, 400, 800}) {
+    const int items = 50000;
+    k1_mma_kernel<<<sms, 128, kSmem>>>(0, items, clk, sink, gap);
+    cudaDeviceSynchronize();
+    long long c = 0;
+    cudaMemcpy(&c, clk, 8, cudaMemcpyDeviceToHost);
+    printf("[gap %4d clk before each burst] %7.0f clk/item (+%.0f over 4 x gap = %d)\n", gap, (double)c / items,
+           (double)c / items - 2881.0, 4 * gap);
+  }
   return 0;
 }

@@ -37,6 +37,16 @@ __global__ void k(float* out, long long* clk, int iters) {
       for (int j = 0; j < 32; j += 2) { __half2 h = __floats2half2_rn(x[j], x[j + 1]); acc ^= *reinterpret_cast<uint32_t*>(&h); }
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] = x[j] * 0.5f - 3.0f + (float)(acc & 1);
+    } else if (MODE == 4) {   // 16 ex2.approx.ftz.f16x2 (= 32 exponentials) + 32 ffma: does the packed form double the MUFU rate?
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        __half2 h = __floats2half2_rn(x[j], x[j + 1]);
+        uint32_t u = *reinterpret_cast<uint32_t*>(&h), r;
+        asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(u));
+        acc ^= r;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = x[j] * 0.5f - 3.0f + (float)(acc & 1);
     } else if (MODE == 3) {   // only 32 ffma (baseline for modes 0/1)
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] = x[j] * 0.5f - 3.0f;
@@ -69,6 +79,7 @@ int main() {
     run<0>("32 MUFU.EX2 + 32 FFMA", w);
     run<1>("16 F2FP.PACK + 32 FFMA", w);
     run<2>("softmax-like chunk", w);
+    run<4>("16 F2FP + 16 EX2.F16x2 + 32 FFMA", w);
   }
   return 0;
 }
