@@ -57,6 +57,7 @@ PROTOTYPES = {
     "ds_debug_set_simmat_blocked": (_i, [_i]),
     "ds_debug_set_attn_mc": (_i, [_i]),
     "ds_debug_set_attn_grid": (_i, [_i]),
+    "ds_debug_set_attn_l2_promotion": (_i, [_i]),
     "ds_attn_fwd": (_i, [Tensor4, Tensor4, Tensor4, _f, Tensor4, _vp, _sz, _vp]),
     "ds_attn_fwd_workspace_bytes": (_sz, [Tensor4, Tensor4]),
     "ds_aas_groups": (_i, [Tensor5, Tensor5, Tensor5, Tensor5, Tensor5, _vp, _vp, _i64, _vp, _i64, _f, _i, _vp, _vp, _sz, _vp]),

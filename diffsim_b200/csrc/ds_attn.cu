@@ -962,6 +962,12 @@ __global__ void matrix_setup_kernel(int64_t n_rows, int64_t n_cols, int chunks, 
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+// ds_debug_set_attn_l2_promotion: L2 fetch granularity of K1's Q / K / V boxes (0 / 64 / 128 / 256 bytes).  A box row is one
+// head's D elements (80-320 bytes) out of a (B, S, H*D) memory row whose other heads are needed much later (streams are
+// head-major): with 256-byte promotion every miss dragged the neighbouring heads' bytes in from DRAM -- 17.1 MB per triplet
+// against 11.8 MB algorithmic at D = 160, 2.9x at DiT's 144-byte rows.  64 bytes: +3% sustained, +5% DiT (gpurun_out/r2bc).
+static int g_attn_l2_promotion = 64;
+
 static int check_t5(const ds_tensor5& t, const char* name) {
   if (!t.ptr) return fail(DS_ERR_INVALID, "%s: null pointer", name);
   if (t.dtype != DS_F16 && t.dtype != DS_BF16) return fail(DS_ERR_UNSUPPORTED, "%s: dtype must be f16 or bf16", name);
@@ -989,7 +995,7 @@ static int make_map(CUtensorMap* m, const ds_tensor5& t, int subw, int rows) {
   };
   uint64_t strides[4] = {st(3), st(2), st(1), st(0)};
   uint32_t box[5] = {(uint32_t)subw, (uint32_t)rows, 1, 1, 1};
-  return encode_tensor_map(m, t.dtype, 5, t.ptr, dims, strides, box, subw * 2);
+  return encode_tensor_map(m, t.dtype, 5, t.ptr, dims, strides, box, subw * 2, g_attn_l2_promotion);
 }
 
 // ds_debug_set_attn_mc: -1 automatic (the N x N matrix only: +2-3% there, -1% sustained and +16% DRAM reads on pair / triplet
@@ -1161,6 +1167,11 @@ int ds_debug_set_trace(void* dev_buf, int cap) {
 #else
   return 0;
 #endif
+}
+
+int ds_debug_set_attn_l2_promotion(int bytes) {
+  if (bytes == 0 || bytes == 64 || bytes == 128 || bytes == 256) ds::g_attn_l2_promotion = bytes;
+  return ds::g_attn_l2_promotion;
 }
 
 int ds_debug_set_attn_grid(int ctas) {

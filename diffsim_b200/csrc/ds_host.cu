@@ -96,7 +96,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int encode_tensor_map(CUtensorMap* out, int dtype, int rank, const void* base, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes, int l2_promotion_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(DS_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
   CUtensorMapDataType dt = dtype == DS_F16    ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
@@ -117,7 +117,11 @@ int encode_tensor_map(CUtensorMap* out, int dtype, int rank, const void* base, c
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
   CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  l2_promotion_bytes >= 256   ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                  : l2_promotion_bytes >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                  : l2_promotion_bytes >= 64  ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                              : CU_TENSOR_MAP_L2_PROMOTION_NONE,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     return fail(DS_ERR_INVALID,

@@ -31,9 +31,11 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (libcuda is not a
 // link-time dependency, so the library loads on a machine without a driver).
 // dims / box: fastest dimension first.  strides_bytes: rank-1 entries (dim 1..).
-// swizzle_bytes: 0, 32, 64 or 128.  Out-of-bounds elements are filled with zero.
+// swizzle_bytes: 0, 32, 64 or 128.  Out-of-bounds elements are filled with zero.  l2_promotion_bytes: 0, 64, 128 or 256 --
+// the granularity at which the L2 fetches a missing box row from DRAM (256 suits rows that are read whole; rows that are
+// thin slices of a wider memory row -- one head of (B, S, H*D) -- would drag their neighbours' bytes in with it).
 int encode_tensor_map(CUtensorMap* out, int dtype, int rank, const void* base, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
+                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes, int l2_promotion_bytes = 256);
 
 // in-stream kernel timing (ds_profile_enable / ds_profile_collect)
 void profile_begin(cudaStream_t st);

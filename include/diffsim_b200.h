@@ -101,6 +101,9 @@ int ds_debug_set_simmat_max_kb(int kb);
  * every K/V tile read from L2 once for both): -1 automatic (default: ds_aas_matrix only, where it measures +2-3%), 0 off,
  * 1 on in every call whose q tile count is even.  Returns the value in force. */
 int ds_debug_set_attn_mc(int mode);
+/* Debug / A-B only: granularity (0, 64, 128 or 256 bytes) at which the L2 fetches a missing row piece of K1's Q / K / V TMA
+ * boxes from DRAM.  Returns the value in force. */
+int ds_debug_set_attn_l2_promotion(int bytes);
 /* Debug / experiments only: cap K1's persistent grid at `ctas` CTAs (0 = default, one CTA per SM) -- how the clocks per item
  * depend on how loaded the chip is.  Returns the value in force. */
 int ds_debug_set_attn_grid(int ctas);
