@@ -44,7 +44,7 @@ sys.path.insert(0, ROOT)
 
 SHAPE = (2, 8, 256, 160)  # SD-1.5 512^2 up_blocks layer 0
 # dram__bytes_read.sum + dram__bytes_write.sum of K1 per triplet, from the ncu --set full capture named in TRAFFIC_SOURCE
-DRAM_BYTES_PER_TRIPLET = (8.747398e9 + 9.337344e6) / 512
+DRAM_BYTES_PER_TRIPLET = (6.052258e9 + 8.091136e6) / 512
 TRAFFIC_SOURCE = ("profiles/r2final_attn_ncu_summary.txt (ncu --set full of this bench at 512 triplets per launch, the round-2 kernel "
                   "as the bench runs it)")
 WORKLOAD = "nights_2afc_triplets_sd15_512_up0_cosine"
