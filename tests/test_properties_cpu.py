@@ -83,3 +83,26 @@ def test_debug_env_switches_are_applied_at_load(monkeypatch):
     finally:
         monkeypatch.delenv("DIFFSIM_B200_DEBUG", raising=False)
         importlib.reload(_native).load().ds_debug_set_simmat_max_kb(256)
+
+
+def test_debug_switches_validate_their_argument_and_report_the_value_in_force():
+    """The A/B switches of include/diffsim_b200.h only store a validated value (no device work): out-of-range arguments are
+    ignored and every call returns what is in force -- which is how the GPU tests restore the defaults."""
+    from diffsim_b200 import _native
+
+    if not os.path.exists(_native.LIB_PATH):
+        pytest.skip("library not built")
+    lib = _native.load()
+    try:
+        assert lib.ds_debug_set_attn_mc(-1) == -1                 # default: multicast for the N x N matrix only
+        assert lib.ds_debug_set_attn_mc(1) == 1 and lib.ds_debug_set_attn_mc(7) == 1 and lib.ds_debug_set_attn_mc(0) == 0
+        assert lib.ds_debug_set_simmat_blocked(-1) == -1
+        assert lib.ds_debug_set_simmat_blocked(1) == 1 and lib.ds_debug_set_simmat_blocked(5) == 1
+        assert lib.ds_debug_set_attn_l2_promotion(64) == 64       # the default
+        assert lib.ds_debug_set_attn_l2_promotion(100) == 64 and lib.ds_debug_set_attn_l2_promotion(256) == 256
+        assert lib.ds_debug_set_attn_grid(0) == 0 and lib.ds_debug_set_attn_grid(-3) == 0 and lib.ds_debug_set_attn_grid(8) == 8
+    finally:
+        lib.ds_debug_set_attn_mc(-1)
+        lib.ds_debug_set_simmat_blocked(-1)
+        lib.ds_debug_set_attn_l2_promotion(64)
+        lib.ds_debug_set_attn_grid(0)
