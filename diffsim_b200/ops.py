@@ -137,7 +137,7 @@ def aas_groups(q: torch.Tensor, k_self: torch.Tensor, v_self: torch.Tensor, k: t
         N.check(lib.ds_aas_groups(q5, _t5(k_self), _t5(v_self), _t5(k), _t5(v), gq.data_ptr(), go.data_ptr(), n_groups,
                                   kv.data_ptr(), n_entries, float(scale) if scale else 0.0, _mode(similarity),
                                   dirs.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)))
-    _count(2)  # attention + finish
+    _count(3)  # index validation + attention + finish
     return dirs
 
 
@@ -156,7 +156,7 @@ def aas_pairs(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, pair_idx, simil
     with torch.cuda.device(dev):
         N.check(lib.ds_aas_pairs(q5, _t5(k), _t5(v), pairs.data_ptr(), P, float(scale) if scale else 0.0,
                                  _mode(similarity), scores.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)))
-    _count(4)  # setup + attention + finish + pair combine
+    _count(5)  # setup + index validation + attention + finish + pair combine
     return scores
 
 
@@ -181,7 +181,7 @@ def aas_triplets(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, trip_idx, si
                                     _mode(similarity), N.DS_OPT_ROUND_SCORES if round_scores else 0, ab.data_ptr(),
                                     ac.data_ptr(), counts.data_ptr(), flags.data_ptr() if want_flags else None,
                                     ws.data_ptr(), ws.numel(), _stream(dev)))
-    _count(4)  # setup + attention + finish + combine/decide
+    _count(5)  # setup + index validation + attention + finish + combine/decide
     return ab, ac, counts, flags
 
 
@@ -260,7 +260,8 @@ def simmat(rows: torch.Tensor, cols: Optional[torch.Tensor] = None, similarity="
         N.check(lib.ds_simmat(rows.data_ptr(), nr, rows.stride(0), cols.data_ptr(), nc, cols.stride(0), L,
                               _dtype_code(rows), _mode(similarity), out.data_ptr(), out.stride(0), ws.data_ptr(),
                               ws.numel(), _stream(dev)))
-    _count(6)  # 2 statistics passes, 2 statistics finishes, GEMM, normalise
+    # statistics pass + its finish per operand (one operand when rows is cols: the symmetric call), GEMM, normalise
+    _count(4 if (cols.data_ptr() == rows.data_ptr() and nr == nc and cols.stride(0) == rows.stride(0)) else 6)
     return out
 
 
